@@ -1,0 +1,241 @@
+"""FakeBob NES attack with the reference's API, executed on the B200.
+
+Mirrors /root/reference FAKEBOB.py:
+  FakeBob.__init__            :21-37   (same hyper-parameters; extra keyword-only knobs below)
+  FakeBob.attack              :139-221 -> device loop (fb_nes_init / fb_nes_run / fb_nes_status)
+  FakeBob.get_grad            :223-246 -> fb_nes_get_grad
+  FakeBob.loss_fn             :248-299 -> same margin losses, evaluated on device inside the loop
+  FakeBob.estimate_threshold  :39-137  -> host control flow, device scoring / gradient / update
+
+Differences a caller can see, all deliberate:
+  * ``rng``: "philox" (default) draws the antithetic Gaussian noise on the GPU with a counter-based
+    generator whose seed is taken from numpy's global generator at construction, so ``np.random.seed``
+    still makes runs reproducible; "numpy" reproduces the reference's stream exactly
+    (``np.random.normal(size=(N, S//2))`` per iteration, FAKEBOB.py:234) at ~90 ms/iteration of host time.
+  * ``model`` must be one of this package's scorers (they carry the resident device models); arbitrary
+    duck-typed black boxes are what the reference's own FAKEBOB.py is for.
+  * per-iteration prints are emitted after each batch of ``iters_per_launch`` iterations.
+"""
+import os
+import pickle
+import time
+
+import numpy as np
+
+UNTARGETED = "untargeted"
+TARGETED = "targeted"
+
+
+class FakeBob(object):
+
+    def __init__(self, task, attack_type, model, adver_thresh=0., epsilon=0.002, max_iter=1000,
+                 max_lr=0.001, min_lr=1e-6, samples_per_draw=50, sigma=0.001, momentum=0.9,
+                 plateau_length=5, plateau_drop=2., *, rng=None, seed=None, verbose=None, iters_per_launch=32):
+        if not hasattr(model, "_engine"):
+            raise TypeError("fakebob_b200.FakeBob needs one of this package's device-backed scorers "
+                            "(gmm_CSI/gmm_OSI/gmm_SV/iv_*); there is no CPU fallback for black-box models")
+        self.task = task
+        self.attack_type = attack_type
+        self.model = model
+        self.adver_thresh = adver_thresh
+        self.epsilon = epsilon
+        self.max_iter = max_iter
+        self.max_lr = max_lr
+        self.min_lr = min_lr
+        self.samples_per_draw = samples_per_draw
+        self.sigma = sigma
+        self.momentum = momentum
+        self.plateau_length = plateau_length
+        self.plateau_drop = plateau_drop
+        self.rng = rng or os.environ.get("FAKEBOB_RNG", "philox")
+        if self.rng not in ("philox", "numpy"):
+            raise ValueError("rng must be 'philox' or 'numpy'")
+        self.seed = int(np.random.randint(0, 2 ** 62)) if seed is None else int(seed)
+        self.verbose = (os.environ.get("FAKEBOB_VERBOSE", "1") != "0") if verbose is None else verbose
+        self.iters_per_launch = max(1, int(iters_per_launch))
+        self.draws = 0                 # Philox draw counter == number of get_grad evaluations so far
+        self.threshold = 0.
+        self.true = None
+        self.target = None
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _column(audio):
+        audio = np.asarray(audio)
+        if len(audio.shape) == 1:
+            audio = audio[:, np.newaxis]
+        elif audio.shape[0] == 1:
+            audio = audio.T
+        return audio
+
+    def _label(self):
+        if self.task == "CSI":
+            return self.target if self.attack_type == TARGETED else self.true
+        if self.task == "OSI" and self.attack_type == TARGETED:
+            return self.target
+        return None
+
+    def _nes_init(self, audio, max_iter):
+        m = self.model
+        eng = m._engine
+        zm = getattr(m, "z_norm_means", None) if self.task == "CSI" or m._fb_arch == "iv" else None
+        zs = getattr(m, "z_norm_stds", None) if zm is not None else None
+        eng.nes_init(audio, self.task, self.attack_type, getattr(m, "n_speakers", 1), self._label(),
+                     self.threshold, self.adver_thresh, self.epsilon, max_iter, self.max_lr, self.min_lr,
+                     self.samples_per_draw, self.sigma, self.momentum, self.plateau_length, self.plateau_drop,
+                     rng=self.rng, seed=self.seed, draw_base=self.draws, z_means=zm, z_stds=zs)
+        return eng
+
+    def _host_noise(self, n):
+        """The reference's draw (FAKEBOB.py:234), re-laid-out pair-major for the device."""
+        pos = np.random.normal(size=(n, self.samples_per_draw // 2))
+        return np.ascontiguousarray(pos.T)
+
+    def _score_row(self, row):
+        s = row[4:]
+        return s[0] if self.task == "SV" else np.array(s)
+
+    # ------------------------------------------------------------------------------------------
+    def attack(self, audio, checkpoint_path, threshold=0., true=None, target=None, fs=16000,
+               bits_per_sample=16, n_jobs=10, debug=False):
+        audio = self._column(audio)
+        self.threshold = threshold
+        self.true = true
+        self.target = target
+        n = audio.shape[0]
+        eng = self._nes_init(audio, self.max_iter)
+        t_start = time.time()
+        done, stopped, printed = 0, False, 0
+        chunk = 1 if self.rng == "numpy" else self.iters_per_launch
+        while not stopped and done < self.max_iter:
+            k = min(chunk, self.max_iter - done)
+            noise = None
+            if self.rng == "numpy":
+                noise = np.stack([self._host_noise(n) for _ in range(k)])
+            eng.nes_run(k, noise)
+            done, stopped = eng.nes_status()
+            if self.verbose:
+                rows = eng.nes_log(done)
+                for it in range(printed, done):
+                    r = rows[it]
+                    print("--- iter %d, distance:%f, loss:%f, score: ---" % (it, r[0], r[1]), self._score_row(r))
+                    if stopped and it == done - 1:
+                        print("------ early stop at iter %d ---" % it)
+                    else:
+                        print("consumption time:%f, lr:%f" % ((time.time() - t_start) / max(done, 1), r[3]))
+                printed = done
+        elapsed = time.time() - t_start
+        rows = eng.nes_log(done)
+        self.draws += done
+        per_iter = elapsed / max(done, 1)
+        cp_global = []
+        for it in range(done):
+            r = rows[it]
+            last_stop = stopped and it == done - 1
+            cp_global.append([r[0], np.array([r[1]]), self._score_row(r), 0. if last_stop else per_iter])
+        if checkpoint_path is not None:
+            with open(checkpoint_path, "wb") as writer:
+                pickle.dump(cp_global, writer, protocol=-1)
+        self.log = rows
+        self.iters_done = done
+        self.elapsed = elapsed
+        last_iter = done - 1
+        success_flag = 1 if last_iter < self.max_iter - 1 else -1
+        adver = eng.nes_adver()[:, np.newaxis]
+        self.final_adver = adver
+        adver = (adver * (2 ** (bits_per_sample - 1))).astype(np.int16)
+        return adver, success_flag
+
+    # ------------------------------------------------------------------------------------------
+    def get_grad(self, audio, fs=16000, bits_per_sample=16, n_jobs=10, debug=False):
+        audio = self._column(audio)
+        eng = self._nes_init(audio, 1)
+        noise = self._host_noise(audio.shape[0]) if self.rng == "numpy" else None
+        final_loss, grad, adver_loss, score0 = eng.nes_get_grad(noise)
+        self.draws += 1
+        score = score0[0] if self.task == "SV" else score0
+        return final_loss, grad[:, np.newaxis], np.array([adver_loss]), score
+
+    def loss_fn(self, audios, fs=16000, bits_per_sample=16, n_jobs=10, debug=False):
+        """Margin losses of FAKEBOB.py:248-299 for an explicit batch (host arithmetic on device scores)."""
+        score = self.model.score(audios, fs=fs, bits_per_sample=bits_per_sample, n_jobs=n_jobs, debug=debug)
+        if self.task in ("OSI", "CSI"):
+            s2 = score if score.ndim == 2 else score[np.newaxis, :]
+            if self.task == "OSI" and self.attack_type != TARGETED:
+                loss = self.threshold + self.adver_thresh - np.max(s2, axis=1, keepdims=True)
+            else:
+                idx = self.target if self.attack_type == TARGETED else self.true
+                other = np.max(np.delete(s2, idx, axis=1), axis=1, keepdims=True)
+                own = s2[:, idx:idx + 1]
+                if self.task == "OSI":
+                    loss = np.maximum(other, self.threshold) + self.adver_thresh - own
+                elif self.attack_type == TARGETED:
+                    loss = other + self.adver_thresh - own
+                else:
+                    loss = own + self.adver_thresh - other
+        else:
+            loss = self.threshold + self.adver_thresh - np.asarray(score).reshape(-1)[:, np.newaxis]
+        return loss, score
+
+    # ------------------------------------------------------------------------------------------
+    def estimate_threshold(self, audio, fs=16000, bits_per_sample=16, n_jobs=10, debug=False):
+        if self.task == "CSI":
+            print("--- Warning: no need to estimate threshold for CSI, quitting ---")
+            return
+        audio = self._column(audio)
+        init_score = self.model.score(audio, fs=fs, bits_per_sample=bits_per_sample, n_jobs=n_jobs, debug=debug)
+        if self.task == "OSI":
+            init_score = np.max(init_score)
+        self.delta = np.abs(init_score / 10)
+        self.threshold = init_score + self.delta
+        attack_type_backup = self.attack_type
+        self.attack_type = UNTARGETED
+        n = audio.shape[0]
+        try:
+            eng = self._nes_init(audio, 1)
+            iter_outer, n_iters, times = 0, 0, 0.
+            while True:
+                if self.verbose:
+                    print("----- iter_outer:%d, threshold:%f -----" % (iter_outer, self.threshold))
+                eng.nes_set_threshold(self.threshold)
+                iter_inner = 0
+                lr = self.max_lr
+                last_ls = []
+                while True:
+                    start = time.time()
+                    adver = eng.nes_adver()[:, np.newaxis]
+                    decision, score = self.model.make_decisions(adver, fs=fs, bits_per_sample=bits_per_sample,
+                                                                n_jobs=n_jobs, debug=debug)
+                    if self.verbose:
+                        print("--- iter_inner:%d, dicision:%d, score: ---" % (iter_inner, decision), score)
+                    if self.task == "OSI":
+                        score = np.max(score)
+                    if decision != -1:
+                        if self.verbose:
+                            print("--- return at iter_outer:%d, iter_inner:%d, return thresh:%f ---" % (iter_outer, iter_inner, score))
+                            print("cost %d iters, %fs time" % (n_iters, times))
+                        return score, n_iters, times
+                    elif score >= self.threshold:
+                        if self.verbose:
+                            print("--- early stop at iter_inner:%d ---" % (iter_inner))
+                        break
+                    noise = self._host_noise(n) if self.rng == "numpy" else None
+                    loss, _, _, _ = eng.nes_get_grad(noise)
+                    self.draws += 1
+                    last_ls.append(loss)
+                    last_ls = last_ls[-self.plateau_length:]
+                    if last_ls[-1] > last_ls[0] and len(last_ls) == self.plateau_length:
+                        if lr > self.min_lr:
+                            lr = max(lr / self.plateau_drop, self.min_lr)
+                        last_ls = []
+                    eng.nes_apply_update(lr)
+                    used_time = time.time() - start
+                    if self.verbose:
+                        print("consumption time:%f, lr:%f" % (used_time, lr))
+                    n_iters += 1
+                    times += used_time
+                    iter_inner += 1
+                self.threshold += self.delta
+                iter_outer += 1
+        finally:
+            self.attack_type = attack_type_backup

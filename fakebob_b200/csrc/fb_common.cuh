@@ -1,0 +1,145 @@
+// Shared declarations for libfakebob_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/fakebob_b200.h"
+
+#define FB_FRAME_LEN   400
+#define FB_FRAME_SHIFT 160
+#define FB_FFT_N       512
+#define FB_NCEPS       24
+#define FB_DIM         72      // 24 x (static, delta, delta-delta)
+#define FB_KSLABS      18      // K = 144 = [x | x^2] in slabs of 8 fp16
+#define FB_TILE_M      128
+#define FB_STAGE_N     64      // W columns per smem stage
+#define FB_CHUNK_N     128     // accumulator columns per (tile, unit)
+#define FB_MAX_MODELS  32
+#define FB_MEL_MAXLEN  48
+
+void fb_set_error(const char *fmt, ...);
+uint64_t fb_alloc_epoch();
+void fb_bump_alloc_epoch();
+
+#define FB_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      fb_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return FB_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define FB_CHECK_ARG(cond, msg)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      fb_set_error("bad argument: %s", msg);    \
+      return FB_ERR_ARG;                        \
+    }                                           \
+  } while (0)
+
+// Device-resident front-end tables (built once per feature config).
+struct FbTables {
+  float  window[FB_FRAME_LEN];
+  float2 tw512[FB_FFT_N];                 // exp(-2 pi i q / 512)
+  int    mel_start[32];
+  int    mel_len[32];
+  float  mel_w[32][FB_MEL_MAXLEN];
+  float  dct[FB_NCEPS][32];               // lifter folded out (applied separately like Kaldi)
+  float  lifter[FB_NCEPS];
+  float  dscale1[7];                      // delta scales (window 3)
+  float  dscale2[13];
+  float  feat_scale[FB_DIM];              // power-of-two per-dimension scale applied before the fp16 split
+  int    num_mel;
+  float  preemph;
+  float  vad_thr, vad_mean_scale, vad_prop;
+  int    vad_ctx;
+  int    cmn_window;
+};
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int ensure(size_t want, bool zero = false) {
+    if (want <= n) return FB_OK;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    fb_bump_alloc_epoch();
+    size_t cap = want + want / 8 + 64;
+    FB_CUDA(cudaMalloc(&p, cap * sizeof(T)));
+    if (zero) FB_CUDA(cudaMemset(p, 0, cap * sizeof(T)));
+    n = cap;
+    return FB_OK;
+  }
+  void release() { if (p) { cudaFree(p); fb_bump_alloc_epoch(); } p = nullptr; n = 0; }
+};
+
+struct FbHostGmm {
+  std::vector<float> weights, means_invvars, inv_vars, gconsts;
+  bool loaded = false;
+};
+
+struct FbNes;   // fb_nes.cu
+struct FbComm;  // fb_comm.cu
+
+struct fb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  fb_feat_config cfg;
+  bool tables_dirty = true;
+  FbTables *tables_dev = nullptr;
+  FbTables tables_host;
+
+  // models
+  FbHostGmm host_gmm[FB_MAX_MODELS];
+  int n_models = 0, C = 0;
+  int gmm_impl = 0;
+  DevBuf<__half> w_img;        // [model][C/64][2][18][64][8]
+  DevBuf<float>  gconst2;      // [model][C]  gconst * log2(e)
+  DevBuf<float>  w_f32;        // [model][C][144] (means_invvars | -0.5 inv_vars), cross-check kernel
+  DevBuf<float>  gconst_nat;   // [model][C]
+
+  // batch workspace (shared by score() calls [tag 0] and the NES state [tag 1])
+  int batch_tag = -1;
+  int B = 0;
+  int64_t total_samples = 0;
+  int total_frames = 0, max_frames = 0;
+  bool debug_feats = false;
+  DevBuf<int16_t> wave;
+  DevBuf<int64_t> wave_off;    // B+1
+  DevBuf<int>     frame_off;   // B+1
+  DevBuf<float>   mfcc;        // [total_frames][24]
+  DevBuf<int>     vrank;       // [total_frames]
+  DevBuf<int>     nvoiced;     // [B]
+  DevBuf<int>     row_off;     // [B+1]
+  DevBuf<int>     misc;        // [0]=ticket, [1]=error flag, [2]=M (total voiced rows)
+  DevBuf<__half>  a_img;       // [n_tiles_pad][2][18][128][8]
+  DevBuf<float>   raw72;       // global fallback scratch for long utterances
+  DevBuf<float>   feats_f32;   // [rows][72] when debug
+  DevBuf<float2>  part;        // [model][C/128][rows_pad] (max, sum) in log2 domain
+  DevBuf<float>   frame_ll;    // [model][rows_pad]
+  DevBuf<double>  avg_ll;      // [B][n_models]
+  std::vector<int64_t> off_host;
+  std::vector<int> frame_off_host;
+  int rows_cap = 0;            // padded row capacity of a_img / part (multiple of 256)
+
+  FbNes *nes = nullptr;
+  FbComm *comm = nullptr;
+  int64_t launches = 0;
+};
+
+// fb_frontend.cu
+int fb_prepare_tables(fb_ctx *ctx);
+int fb_reserve_batch(fb_ctx *ctx, int B, const int64_t *offsets_host);
+int fb_run_frontend(fb_ctx *ctx);             // mfcc -> vad_scan -> feats (wave already on device)
+// fb_gmm.cu
+int fb_run_gmm(fb_ctx *ctx);                  // gmm -> reduce into avg_ll
+// helpers
+static inline int fb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

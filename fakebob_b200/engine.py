@@ -1,0 +1,241 @@
+"""Host-side engine: owns one ``fb_ctx`` (one GPU, one stream), the resident GMM parameters and the
+NES attack state.  This is what replaces ``gmm_ubm_kaldiHelper`` on the hot path
+(``gmm_ubm_kaldiHelper.py:270-291``): no wav/ark/text files, no subprocesses -- one C-ABI call per
+batch of audios, or per K NES iterations.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib, kaldi_io
+from .config import FeatureConfig
+
+
+def default_device():
+    for k in ("FAKEBOB_DEVICE", "LOCAL_RANK"):
+        if k in os.environ:
+            return int(os.environ[k])
+    return 0
+
+
+def to_audio_list(audios, bits_per_sample=16):
+    """Input conventions of the reference's score() (gmm_ubm_OSI.py:70-85): ndarray (N,), (N,1), (1,N) is
+    one audio; (N,B) is B audios as columns; otherwise a list of 1-D arrays of possibly different
+    lengths.  Non-int16 data is scaled by 2**(bits-1) and truncated toward zero.  Single 2-D audios
+    are flattened."""
+    if isinstance(audios, np.ndarray):
+        if audios.ndim == 1 or (audios.ndim == 2 and (audios.shape[0] == 1 or audios.shape[1] == 1)):
+            lst = [audios.reshape(-1)]
+        elif audios.ndim == 2:
+            lst = [audios[:, i] for i in range(audios.shape[1])]
+        else:
+            raise ValueError("audios must be a 1-D or 2-D array or a list of 1-D arrays")
+    else:
+        lst = [np.asarray(a).reshape(-1) for a in audios]
+    out = []
+    for a in lst:
+        if a.dtype != np.int16:
+            a = (a * (2 ** (bits_per_sample - 1))).astype(np.int16)
+        out.append(np.ascontiguousarray(a))
+    return out
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class GmmEngine:
+    """Resident diagonal GMMs + front-end on one B200."""
+
+    def __init__(self, gmm_params, feat_cfg=None, device=None):
+        """gmm_params: list of dicts(weights, means_invvars, inv_vars, gconsts) in scoring order."""
+        self.lib = _lib.load()
+        self.device = default_device() if device is None else device
+        self.cfg = feat_cfg or FeatureConfig()
+        self.cfg.check_supported()
+        h = C.c_void_p()
+        _lib.check(self.lib.fb_ctx_create(self.device, C.byref(h)))
+        self.h = h
+        fc = _lib.FeatConfig(self.cfg.sample_frequency, self.cfg.low_freq, self.cfg.high_freq, self.cfg.num_mel_bins,
+                             self.cfg.num_ceps, self.cfg.preemph, self.cfg.cepstral_lifter,
+                             self.cfg.vad_energy_threshold, self.cfg.vad_energy_mean_scale,
+                             self.cfg.vad_proportion_threshold, self.cfg.vad_frames_context, self.cfg.cmn_window)
+        _lib.check(self.lib.fb_set_feature_config(self.h, C.byref(fc)))
+        self.n_models = len(gmm_params)
+        for slot, g in enumerate(gmm_params):
+            w = np.ascontiguousarray(g["weights"], dtype=np.float32)
+            miv = np.ascontiguousarray(g["means_invvars"], dtype=np.float32)
+            iv = np.ascontiguousarray(g["inv_vars"], dtype=np.float32)
+            gc = np.ascontiguousarray(g["gconsts"], dtype=np.float32)
+            Cn, D = miv.shape
+            _lib.check(self.lib.fb_load_diag_gmm(self.h, slot, _ptr(w), _ptr(miv), _ptr(iv), _ptr(gc), Cn, D))
+        _lib.check(self.lib.fb_finalize_gmms(self.h, self.n_models))
+        self._nes_keep = None
+        self._last_B = 0
+
+    @classmethod
+    def from_files(cls, paths, feat_cfg=None, device=None):
+        return cls([kaldi_io.read_diag_gmm(p) for p in paths], feat_cfg=feat_cfg, device=device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scoring ---------------------------------------------------------------------------------
+    def score_avg_ll(self, audio_list):
+        """list of int16 1-D arrays -> (B, n_models) float64 average frame log-likelihoods."""
+        B = len(audio_list)
+        if B == 0:
+            return np.zeros((0, self.n_models))
+        lens = np.array([a.shape[0] for a in audio_list], dtype=np.int64)
+        offsets = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        wave = np.concatenate(audio_list) if B > 1 else audio_list[0]
+        wave = np.ascontiguousarray(wave, dtype=np.int16)
+        out = np.empty((B, self.n_models), dtype=np.float64)
+        _lib.check(self.lib.fb_score_gmm_host(self.h, _ptr(wave), _ptr(offsets), B, _ptr(out)))
+        self._last_B = B
+        self._last_offsets = offsets
+        return out
+
+    def set_debug(self, on=True):
+        _lib.check(self.lib.fb_set_debug(self.h, 1 if on else 0))
+
+    def set_gmm_impl(self, impl):
+        _lib.check(self.lib.fb_set_gmm_impl(self.h, {"umma": 0, "tcgen05": 0, "simt": 1}.get(impl, impl)))
+
+    def last_stages(self):
+        """Per-stage outputs of the last score call (parity tests): dict(frames, voiced, mfcc, vad, feats, frame_ll)."""
+        B = self._last_B
+        frames = np.zeros(B, dtype=np.int32)
+        voiced = np.zeros(B, dtype=np.int32)
+        _lib.check(self.lib.fb_get_num_frames(self.h, B, _ptr(frames), _ptr(voiced)))
+        T = int(frames.sum())
+        mf = np.empty((T, 24), dtype=np.float32)
+        _lib.check(self.lib.fb_get_mfcc(self.h, _ptr(mf), mf.size))
+        vad = np.empty(T, dtype=np.int32)
+        _lib.check(self.lib.fb_get_vad(self.h, _ptr(vad), vad.size))
+        rows = int(voiced.sum())
+        out = {"frames": frames, "voiced": voiced, "mfcc": mf, "vad": vad}
+        fl = np.empty((self.n_models, rows), dtype=np.float32)
+        _lib.check(self.lib.fb_get_frame_loglikes(self.h, _ptr(fl), fl.size))
+        out["frame_ll"] = fl
+        try:
+            ft = np.empty((rows, 72), dtype=np.float32)
+            _lib.check(self.lib.fb_get_features(self.h, _ptr(ft), ft.size))
+            out["feats"] = ft
+        except _lib.FakebobLibraryError:
+            out["feats"] = None
+        return out
+
+    def features(self, wave_int16):
+        """(Tv, 72) float32 front-end output for one utterance (used to build synthetic models on the GPU)."""
+        self.set_debug(True)
+        self.score_avg_ll([np.ascontiguousarray(wave_int16, dtype=np.int16)])
+        return self.last_stages()["feats"]
+
+    # ---- NES -------------------------------------------------------------------------------------
+    def nes_init(self, audio, task, attack_type, n_speakers, label, threshold, adver_thresh, epsilon, max_iter,
+                 max_lr, min_lr, samples_per_draw, sigma, momentum, plateau_length, plateau_drop,
+                 rng="philox", seed=0, draw_base=0, z_means=None, z_stds=None):
+        audio = np.ascontiguousarray(np.asarray(audio, dtype=np.float64).reshape(-1))
+        p = _lib.NesParams()
+        p.task = _lib.TASK[task]
+        p.targeted = 1 if attack_type == "targeted" else 0
+        p.label = -1 if label is None else int(label)
+        p.n_speakers = n_speakers
+        p.samples_per_draw = samples_per_draw
+        p.max_iter = max_iter
+        p.rng = _lib.RNG[rng]
+        p.plateau_length = plateau_length
+        p.threshold, p.adver_thresh, p.epsilon, p.sigma = threshold, adver_thresh, epsilon, sigma
+        p.max_lr, p.min_lr, p.momentum, p.plateau_drop = max_lr, min_lr, momentum, plateau_drop
+        p.seed, p.draw_base = seed, draw_base
+        keep = [audio]
+        if z_means is not None:
+            zm = np.ascontiguousarray(z_means, dtype=np.float64)
+            zs = np.ascontiguousarray(z_stds, dtype=np.float64)
+            p.z_norm_means = zm.ctypes.data_as(C.POINTER(C.c_double))
+            p.z_norm_stds = zs.ctypes.data_as(C.POINTER(C.c_double))
+            keep += [zm, zs]
+        _lib.check(self.lib.fb_nes_init(self.h, C.byref(p), _ptr(audio), audio.shape[0]))
+        self._nes_keep = keep
+        self._nes_N = audio.shape[0]
+        self._nes_K = n_speakers
+        self._nes_S2 = samples_per_draw // 2
+
+    def nes_run(self, n_iters, noise=None):
+        """noise (host rng): (n_iters, S/2, N) float64, pair-major."""
+        if noise is not None:
+            noise = np.ascontiguousarray(noise, dtype=np.float64)
+            assert noise.shape == (n_iters, self._nes_S2, self._nes_N)
+        _lib.check(self.lib.fb_nes_run(self.h, n_iters, _ptr(noise) if noise is not None else None))
+
+    def nes_status(self):
+        it, st = C.c_int(0), C.c_int(0)
+        _lib.check(self.lib.fb_nes_status(self.h, C.byref(it), C.byref(st)))
+        return it.value, bool(st.value)
+
+    def nes_log(self, max_rows):
+        rows = np.zeros((max_rows, 4 + self._nes_K), dtype=np.float64)
+        n = _lib.check(self.lib.fb_nes_read_log(self.h, _ptr(rows), max_rows))
+        return rows[:n]
+
+    def nes_adver(self):
+        a = np.empty(self._nes_N, dtype=np.float64)
+        _lib.check(self.lib.fb_nes_read_adver(self.h, _ptr(a), a.shape[0]))
+        return a
+
+    def nes_grad(self):
+        a = np.empty(self._nes_N, dtype=np.float64)
+        _lib.check(self.lib.fb_nes_read_grad(self.h, _ptr(a), a.shape[0]))
+        return a
+
+    def nes_set_threshold(self, threshold):
+        _lib.check(self.lib.fb_nes_set_threshold(self.h, float(threshold)))
+
+    def nes_get_grad(self, noise=None):
+        """-> (final_loss, grad (N,), adver_loss, score0 (K,)).  noise (host rng): (S/2, N) float64."""
+        if noise is not None:
+            noise = np.ascontiguousarray(noise, dtype=np.float64)
+            assert noise.shape == (self._nes_S2, self._nes_N)
+        fl, al = C.c_double(0), C.c_double(0)
+        sc = np.zeros(self._nes_K, dtype=np.float64)
+        g = np.empty(self._nes_N, dtype=np.float64)
+        _lib.check(self.lib.fb_nes_get_grad(self.h, _ptr(noise) if noise is not None else None,
+                                            C.byref(fl), C.byref(al), _ptr(sc), _ptr(g)))
+        return fl.value, g, al.value, sc
+
+    def nes_apply_update(self, lr):
+        _lib.check(self.lib.fb_nes_apply_update(self.h, float(lr)))
+
+    def kernel_launches(self):
+        n = C.c_int64(0)
+        _lib.check(self.lib.fb_nes_kernel_launches(self.h, C.byref(n)))
+        return n.value
+
+    def synchronize(self):
+        _lib.check(self.lib.fb_synchronize(self.h))
+
+    # ---- multi-GPU ---------------------------------------------------------------------------------
+    def comm_init_from_torch(self):
+        """Create the NCCL communicator for this engine using torch.distributed for the id exchange."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if world == 1:
+            return
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            _lib.check(self.lib.fb_comm_unique_id(buf))
+        obj = [bytes(buf)]
+        dist.broadcast_object_list(obj, src=0)
+        ident = (C.c_char * 128).from_buffer_copy(obj[0])
+        _lib.check(self.lib.fb_comm_init(self.h, ident, rank, world))

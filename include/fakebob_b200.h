@@ -1,0 +1,148 @@
+/*
+ * fakebob_b200 -- C ABI of the B200-native FAKEBOB hot path (libfakebob_b200.so).
+ *
+ * The reference has no FFI: its extension point is Python duck typing
+ * (README.md:136 "function score and make_decisions") and every scorer shells out to
+ * Kaldi binaries through gmm_ubm_kaldiHelper / ivector_PLDA_kaldiHelper.  This header
+ * is the boundary a binding for that path needs: each entry point names the reference
+ * call it replaces.  Plain C, caller-owned buffers, explicit sizes, int return codes
+ * (0 = ok, negative = error, text via fb_last_error()).  No torch / C++ types cross it.
+ * A context is bound to one CUDA device and one stream; a context is not thread-safe,
+ * different contexts are independent.
+ *
+ * Conventions
+ *   - "host" pointers are CPU memory, "dev" pointers are device memory on the context's GPU.
+ *   - audio is 16-bit PCM exactly as the reference writes it to <i>.wav
+ *     (gmm_ubm_kaldiHelper.py:56-68) after (x * 2^15).astype(int16) (gmm_ubm_OSI.py:83-85).
+ *   - utterance b of a batch occupies samples [offsets[b], offsets[b+1]) of `wave`.
+ */
+#ifndef FAKEBOB_B200_H
+#define FAKEBOB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fb_ctx fb_ctx;
+
+/* ---- errors / lifetime ------------------------------------------------------------ */
+#define FB_OK               0
+#define FB_ERR_CUDA        -1
+#define FB_ERR_ARG         -2
+#define FB_ERR_STATE       -3
+#define FB_ERR_NO_VOICED   -4   /* an utterance has zero voiced frames (Kaldi would drop it) */
+#define FB_ERR_NCCL        -5
+#define FB_ERR_UNSUPPORTED -6
+
+const char *fb_last_error(void);
+int  fb_version(void);
+int  fb_ctx_create(int device, fb_ctx **out);
+int  fb_ctx_destroy(fb_ctx *ctx);
+/* cudaStream_t passed as void*; NULL = the context's own stream. */
+int  fb_set_stream(fb_ctx *ctx, void *cuda_stream);
+int  fb_synchronize(fb_ctx *ctx);
+
+/* ---- feature configuration --------------------------------------------------------
+ * Replaces: --config=conf/mfcc.conf (gmm_ubm_kaldiHelper.py:138), --vad-config conf/vad.conf (:158),
+ * delta_opts (:191-193), apply-cmvn-sliding options (:196). */
+typedef struct fb_feat_config {
+  float sample_frequency;      /* 16000 */
+  float low_freq, high_freq;   /* 20, 7600 */
+  int   num_mel_bins;          /* 30 (<= 32) */
+  int   num_ceps;              /* 24 (fixed by the kernels) */
+  float preemph;               /* 0.97 */
+  float cepstral_lifter;       /* 22 */
+  float vad_energy_threshold;  /* 5.5 */
+  float vad_energy_mean_scale; /* 0.5 */
+  float vad_proportion_threshold; /* 0.12 */
+  int   vad_frames_context;    /* 2 */
+  int   cmn_window;            /* 300 */
+} fb_feat_config;
+int fb_set_feature_config(fb_ctx *ctx, const fb_feat_config *cfg);
+
+/* ---- diagonal GMMs ---------------------------------------------------------------
+ * Replaces: the model rxfilename argument of gmm-global-get-frame-likes
+ * (gmm_ubm_kaldiHelper.py:206-208); arrays are Kaldi's stored DiagGmm members
+ * (host, float32, row-major C x D).  Slots are scored in slot order.  All slots must share C and D=72. */
+int fb_load_diag_gmm(fb_ctx *ctx, int slot, const float *weights, const float *means_invvars,
+                     const float *inv_vars, const float *gconsts, int C, int D);
+int fb_finalize_gmms(fb_ctx *ctx, int n_models);
+/* 0 = tcgen05 tensor-core kernel (default), 1 = fp32 CUDA-core cross-check kernel. */
+int fb_set_gmm_impl(fb_ctx *ctx, int impl);
+
+/* ---- batch scoring: serves gmm_{CSI,OSI,SV}.score() --------------------------------
+ * Replaces: gmm_ubm_kaldiHelper.score() (gmm_ubm_kaldiHelper.py:270-291): write_audio, data_prepare,
+ * make_mfcc, compute_vad, get_frames_likes, resolce_scores.
+ * out_avg_ll[b * n_models + k] = average per-voiced-frame log-likelihood of utterance b under slot k
+ * (what `gmm-global-get-frame-likes --average=true` prints), float64.
+ * _host: pageable or pinned host buffers, copies included, synchronous.
+ * _dev : device buffers, asynchronous on the context's stream. */
+int fb_score_gmm_host(fb_ctx *ctx, const int16_t *wave, const int64_t *offsets, int B, double *out_avg_ll);
+int fb_score_gmm_dev(fb_ctx *ctx, const int16_t *wave_dev, const int64_t *offsets_host, int B, double *out_avg_ll_dev);
+
+/* ---- stage read-backs (used by the parity tests; valid after a score call) ------------ */
+int fb_set_debug(fb_ctx *ctx, int keep_f32_features);
+int fb_get_num_frames(fb_ctx *ctx, int B, int32_t *frames_host, int32_t *voiced_host);
+int fb_get_mfcc(fb_ctx *ctx, float *out_host, int64_t capacity_floats);          /* [sum T_b][24] */
+int fb_get_vad(fb_ctx *ctx, int32_t *out_host, int64_t capacity);                /* [sum T_b] rank or -1 */
+int fb_get_features(fb_ctx *ctx, float *out_host, int64_t capacity_floats);      /* [sum Tv_b][72], needs debug */
+int fb_get_frame_loglikes(fb_ctx *ctx, float *out_host, int64_t capacity_floats);/* [n_models][sum Tv_b] */
+
+/* ---- NES attack state: serves FakeBob.attack()/get_grad()/estimate_threshold() --------
+ * Replaces: the body of the loop at FAKEBOB.py:168-214 (get_grad :223-246, loss_fn :248-299,
+ * momentum :193, plateau LR :195-200, sign step + clip :202-203, early stop :181, log rows :209-214). */
+enum { FB_TASK_CSI = 0, FB_TASK_OSI = 1, FB_TASK_SV = 2 };
+enum { FB_RNG_HOST = 0, FB_RNG_PHILOX = 1 };
+
+typedef struct fb_nes_params {
+  int    task;               /* FB_TASK_* */
+  int    targeted;           /* 1 = targeted */
+  int    label;              /* target (targeted) or true (CSI untargeted) speaker index; -1 if unused */
+  int    n_speakers;         /* K; model slots are [ubm, spk_0..spk_{K-1}] for OSI/SV, [spk_0..] for CSI */
+  int    samples_per_draw;   /* S; S/2 antithetic pairs (odd S uses S-1, FAKEBOB.py:234-235) */
+  int    max_iter;
+  int    rng;                /* FB_RNG_* */
+  int    plateau_length;
+  double threshold;          /* theta */
+  double adver_thresh;       /* kappa */
+  double epsilon, sigma, max_lr, min_lr, momentum, plateau_drop;
+  uint64_t seed;             /* Philox key */
+  uint64_t draw_base;        /* Philox iteration counter of the first draw */
+  const double *z_norm_means;/* CSI only, host, K */
+  const double *z_norm_stds; /* CSI only, host, K */
+} fb_nes_params;
+
+/* Creates device state for one utterance of n_samples (float64 audio in [-1,1], host). */
+int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *audio_host, int64_t n_samples);
+/* Change theta / label / attack type without re-uploading the audio (estimate_threshold outer loop). */
+int fb_nes_set_threshold(fb_ctx *ctx, double threshold);
+/* Enqueue up to n_iters iterations (stops early on device when adver_loss < 0).  rng = HOST: noise_host
+ * is n_iters x (S/2) x n_samples float64 (pair-major), else NULL.  Asynchronous. */
+int fb_nes_run(fb_ctx *ctx, int n_iters, const double *noise_host);
+/* Blocks until enqueued work finished; returns iterations executed so far and whether early stop hit. */
+int fb_nes_status(fb_ctx *ctx, int *iters_done, int *stopped);
+/* Log rows [iter] = {distance, adver_loss, final_loss, lr, score_0..score_{K-1}} (float64, 4+K per row). */
+int fb_nes_read_log(fb_ctx *ctx, double *rows_host, int max_rows);
+int fb_nes_read_adver(fb_ctx *ctx, double *adver_host, int64_t n_samples);
+int fb_nes_read_grad(fb_ctx *ctx, double *grad_host, int64_t n_samples);
+/* One gradient estimate without the update: FakeBob.get_grad (FAKEBOB.py:223-246). */
+int fb_nes_get_grad(fb_ctx *ctx, const double *noise_host, double *final_loss, double *adver_loss,
+                    double *score0_host, double *grad_host);
+/* adver <- clip(adver - lr*sign(momentum*grad + (1-momentum)*g), lower, upper) with g from the last get_grad. */
+int fb_nes_apply_update(fb_ctx *ctx, double lr);
+int fb_nes_kernel_launches(fb_ctx *ctx, int64_t *count);
+
+/* ---- multi-GPU: one process per GPU, antithetic pairs sharded across ranks ---------------
+ * New (nothing in the reference communicates): a single ncclAllReduce(sum, float64) of
+ * [grad partial (N) | losses (S+1) | score_0 (K)] per iteration on the context's stream.
+ * The unique id is produced by rank 0 and distributed by the host (torch.distributed). */
+int fb_comm_unique_id(void *out_128_bytes);
+int fb_comm_init(fb_ctx *ctx, const void *unique_id_128_bytes, int rank, int world);
+int fb_comm_destroy(fb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAKEBOB_B200_H */

@@ -1,0 +1,135 @@
+"""GPU parity tests for the GMM-UBM scoring path, through the C-ABI (fb_score_gmm_host) and the
+reference-named Python wrappers.  Oracle = oracle/ (numpy restatement of the Kaldi arithmetic)."""
+import numpy as np
+import pytest
+
+from conftest import test_audio as make_audio
+
+pytestmark = pytest.mark.gpu
+
+# float tolerances (float32 pipelines with different summation orders / FFT algorithms)
+TOL_MFCC = 2e-3        # absolute, on cepstra of magnitude <= ~60 (log of near-zero mel energies amplifies rounding)
+TOL_FEAT = 2e-3
+TOL_FRAME_LL = 2e-3    # absolute, per-frame log-likelihood of magnitude ~100
+TOL_AVG_LL = 5e-4      # absolute, per-utterance average log-likelihood
+TOL_SCORE = 5e-4       # absolute, LLR score (difference of two averages)
+
+
+@pytest.fixture(scope="module")
+def osi(small_tree):
+    from fakebob_b200.gmm_ubm_OSI import gmm_OSI
+    m = gmm_OSI(small_tree["root"] + "/grp-osi", small_tree["models"], small_tree["ubm"],
+                pre_model_dir=small_tree["pre_model_dir"], threshold=0.1)
+    m._engine.set_debug(True)
+    return m
+
+
+def _oracle_stages(w, cfg=None):
+    from oracle import kaldi_feats as kf
+    m = kf.mfcc(w)
+    v = kf.compute_vad(m)
+    f = kf.sliding_cmn(kf.add_deltas(m))
+    return m, v, f[v != 0]
+
+
+def test_frontend_stages_match_oracle(osi):
+    from fakebob_b200.engine import to_audio_list
+    audios = [make_audio(3, 0), make_audio(4, 1, n=24000), make_audio(5, 2, n=40001)]
+    lst = to_audio_list(audios)
+    osi._engine.score_avg_ll(lst)
+    st = osi._engine.last_stages()
+    f0 = 0
+    r0 = 0
+    for b, w in enumerate(lst):
+        m, v, f = _oracle_stages(w)
+        T = m.shape[0]
+        assert st["frames"][b] == T
+        gm = st["mfcc"][f0:f0 + T]
+        assert np.abs(gm - m).max() < TOL_MFCC
+        gv = (st["vad"][f0:f0 + T] >= 0).astype(np.float32)
+        # VAD may only differ where C0 is within rounding of the threshold
+        assert (gv != v).sum() <= 1
+        if (gv == v).all():
+            Tv = int(v.sum())
+            assert st["voiced"][b] == Tv
+            gf = st["feats"][r0:r0 + Tv]
+            assert np.abs(gf - f).max() < TOL_FEAT
+        f0 += T
+        r0 += int(st["voiced"][b])
+
+
+def test_frame_loglikes_match_oracle(osi, small_oracle_models):
+    from fakebob_b200.engine import to_audio_list
+    ubm, spk = small_oracle_models
+    lst = to_audio_list([make_audio(7, 1)])
+    avg = osi._engine.score_avg_ll(lst)
+    st = osi._engine.last_stages()
+    X = st["feats"]
+    for k, g in enumerate([ubm] + spk):
+        ref = g.frame_loglikes(X)
+        assert np.abs(st["frame_ll"][k] - ref).max() < TOL_FRAME_LL
+        assert abs(avg[0, k] - float(g.avg_loglike(X))) < TOL_AVG_LL
+
+
+def test_umma_matches_simt_cross_check(osi):
+    from fakebob_b200.engine import to_audio_list
+    lst = to_audio_list([make_audio(8, 0), make_audio(9, 2)])
+    a = osi._engine.score_avg_ll(lst)
+    fa = osi._engine.last_stages()["frame_ll"].copy()
+    osi._engine.set_gmm_impl("simt")
+    try:
+        b = osi._engine.score_avg_ll(lst)
+        fb = osi._engine.last_stages()["frame_ll"].copy()
+    finally:
+        osi._engine.set_gmm_impl("umma")
+    assert np.abs(fa - fb).max() < 1e-3
+    assert np.abs(a - b).max() < 2e-4
+
+
+def test_osi_scores_match_oracle(osi, small_oracle_models):
+    from oracle.scorers import OracleGmmOSI
+    ubm, spk = small_oracle_models
+    ref = OracleGmmOSI(ubm, spk, threshold=0.1)
+    batch = np.stack([make_audio(s, s % 3) for s in range(11, 16)], axis=1)      # (N, B) columns
+    got = osi.score(batch)
+    want = ref.score(batch)
+    assert got.shape == want.shape == (5, 3)
+    assert np.abs(got - want).max() < TOL_SCORE
+    d1, s1 = osi.make_decisions(batch)
+    d2, s2 = ref.make_decisions(batch)
+    assert list(d1) == list(d2)
+    one = osi.score(batch[:, 0])
+    assert one.shape == (3,)
+    assert np.abs(one - want[0]).max() < TOL_SCORE
+
+
+def test_csi_sv_wrappers(small_tree, small_oracle_models):
+    from fakebob_b200.gmm_ubm_CSI import gmm_CSI
+    from fakebob_b200.gmm_ubm_SV import gmm_SV
+    from oracle.scorers import OracleGmmCSI, OracleGmmSV
+    ubm, spk = small_oracle_models
+    models = small_tree["models"]
+    csi = gmm_CSI(small_tree["root"] + "/grp-csi", models, pre_model_dir=small_tree["pre_model_dir"])
+    ref = OracleGmmCSI(spk, [m[3] for m in models], [m[4] for m in models])
+    lst = [make_audio(21, 0), make_audio(22, 1, n=20000)]
+    got, want = csi.score(lst), ref.score(lst)
+    assert got.shape == want.shape == (2, 3)
+    assert np.abs(got - want).max() < 1e-3
+    assert csi.make_decisions(lst)[0] == ref.make_decisions(lst)[0]
+    sv = gmm_SV(small_tree["root"] + "/spk-sv", models[1], small_tree["ubm"], pre_model_dir=small_tree["pre_model_dir"], threshold=0.0)
+    rsv = OracleGmmSV(ubm, spk[1])
+    g1, w1 = sv.score(lst), rsv.score(lst)
+    assert g1.shape == (2,) and np.abs(g1 - w1).max() < TOL_SCORE
+    g2 = sv.score(lst[0])
+    assert np.isscalar(g2) or g2.shape == ()
+    dec, _ = sv.make_decisions(lst[0])
+    assert dec in (1, -1)
+
+
+def test_no_voiced_frames_raises(osi):
+    from fakebob_b200._lib import FakebobLibraryError
+    silent = np.zeros(16000, dtype=np.int16)
+    silent[::7] = 1
+    # constant-energy audio: every frame has the same log-energy, none exceeds 5.5 + 0.5*mean when tiny
+    with pytest.raises(FakebobLibraryError):
+        osi.score([silent])
