@@ -64,6 +64,9 @@ _SIGS = {
     "fb_nes_get_grad": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P]),
     "fb_nes_apply_update": (C.c_int, [_P, C.c_double]),
     "fb_nes_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "fb_profile_enable": (C.c_int, [_P, C.c_int]),
+    "fb_profile_read": (C.c_int, [_P, _P, _P]),
+    "fb_get_voiced_rows": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "fb_comm_unique_id": (C.c_int, [_P]),
     "fb_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "fb_comm_destroy": (C.c_int, [_P]),

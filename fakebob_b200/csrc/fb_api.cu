@@ -154,6 +154,7 @@ extern "C" int fb_score_gmm_host(fb_ctx *ctx, const int16_t *wave, const int64_t
   if ((rc = score_common(ctx, offsets, B))) return rc;
   if ((rc = ctx->wave.ensure((size_t)offsets[B] + 8))) return rc;
   FB_CUDA(cudaMemcpyAsync(ctx->wave.p, wave, (size_t)offsets[B] * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  fb_prof_mark(ctx, -1);
   if ((rc = fb_run_frontend_flag(ctx, nullptr))) return rc;
   if ((rc = fb_run_gmm_flag(ctx, nullptr))) return rc;
   FB_CUDA(cudaMemcpyAsync(out_avg_ll, ctx->avg_ll.p, (size_t)B * ctx->n_models * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -230,4 +231,54 @@ extern "C" int fb_get_frame_loglikes(fb_ctx *ctx, float *out_host, int64_t capac
     FB_CUDA(cudaMemcpy(out_host + (size_t)m * rows, ctx->frame_ll.p + (size_t)m * ctx->rows_cap, (size_t)rows * sizeof(float),
                        cudaMemcpyDeviceToHost));
   return rows;
+}
+
+// ---- profiler -----------------------------------------------------------------------------------
+void fb_prof_mark(fb_ctx *ctx, int tag) {
+  if (!ctx->prof_on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, ctx->stream);
+  ctx->prof_ev.push_back(e);
+  ctx->prof_tag.push_back(tag);
+}
+
+static void prof_drain(fb_ctx *ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  for (size_t i = 1; i < ctx->prof_ev.size(); ++i) {
+    const int tag = ctx->prof_tag[i];
+    if (tag < 0 || tag >= FB_PROF_STAGES) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->prof_ev[i - 1], ctx->prof_ev[i]) == cudaSuccess) {
+      ctx->prof_ms[tag] += ms;
+      ctx->prof_cnt[tag] += 1;
+    }
+  }
+  for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+  ctx->prof_ev.clear();
+  ctx->prof_tag.clear();
+}
+
+extern "C" int fb_profile_enable(fb_ctx *ctx, int on) {
+  FB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  prof_drain(ctx);
+  ctx->prof_on = on != 0;
+  if (on) {
+    memset(ctx->prof_ms, 0, sizeof(ctx->prof_ms));
+    memset(ctx->prof_cnt, 0, sizeof(ctx->prof_cnt));
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_profile_read(fb_ctx *ctx, double *ms_host, int64_t *count_host) {
+  FB_CHECK_ARG(ctx && ms_host && count_host, "NULL argument");
+  prof_drain(ctx);
+  memcpy(ms_host, ctx->prof_ms, sizeof(ctx->prof_ms));
+  memcpy(count_host, ctx->prof_cnt, sizeof(ctx->prof_cnt));
+  return FB_OK;
+}
+
+extern "C" int fb_get_voiced_rows(fb_ctx *ctx, int *rows) {
+  FB_CHECK_ARG(ctx && rows, "NULL argument");
+  return total_rows(ctx, rows);
 }

@@ -130,6 +130,13 @@ struct fb_ctx {
   std::vector<int> frame_off_host;
   int rows_cap = 0;            // padded row capacity of a_img / part (multiple of 256)
 
+  // per-stage profiler
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_tag;      // stage id closed by event i (event 0 of a sequence has tag -1)
+  double prof_ms[FB_PROF_STAGES] = {0};
+  int64_t prof_cnt[FB_PROF_STAGES] = {0};
+
   FbNes *nes = nullptr;
   FbComm *comm = nullptr;
   int64_t launches = 0;
@@ -141,5 +148,6 @@ int fb_reserve_batch(fb_ctx *ctx, int B, const int64_t *offsets_host);
 int fb_run_frontend(fb_ctx *ctx);             // mfcc -> vad_scan -> feats (wave already on device)
 // fb_gmm.cu
 int fb_run_gmm(fb_ctx *ctx);                  // gmm -> reduce into avg_ll
+void fb_prof_mark(fb_ctx *ctx, int tag);
 // helpers
 static inline int fb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -499,8 +499,10 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   dim3 g1(fb_div_up(ctx->max_frames, MFCC_WARPS), B);
   mfcc_kernel<<<g1, MFCC_WARPS * 32, 0, ctx->stream>>>(ctx->wave.p, ctx->wave_off.p, ctx->frame_off.p, ctx->tables_dev,
                                                        ctx->mfcc.p, done_flag);
+  fb_prof_mark(ctx, 1);
   vad_scan_kernel<<<B, 256, 0, ctx->stream>>>(ctx->mfcc.p, ctx->frame_off.p, ctx->tables_dev, ctx->vrank.p,
                                               ctx->nvoiced.p, ctx->row_off.p, ctx->misc.p, B, done_flag);
+  fb_prof_mark(ctx, 2);
   const size_t smem = (size_t)ctx->max_frames * FB_DIM * sizeof(float);
   const int use_smem = smem <= 200 * 1024;
   static size_t configured = 0;
@@ -511,6 +513,7 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   feats_kernel<<<B, FEATS_THREADS, use_smem ? smem : 0, ctx->stream>>>(
       ctx->mfcc.p, ctx->frame_off.p, ctx->vrank.p, ctx->row_off.p, ctx->tables_dev, ctx->a_img.p,
       ctx->debug_feats ? ctx->feats_f32.p : nullptr, use_smem ? nullptr : ctx->raw72.p, use_smem, done_flag);
+  fb_prof_mark(ctx, 3);
   ctx->launches += 3;
   FB_CUDA(cudaGetLastError());
   return FB_OK;

@@ -510,9 +510,11 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
                                                    ctx->tables_dev->feat_scale, ctx->part.p, ctx->misc.p,
                                                    ctx->n_models, ctx->C, ctx->rows_cap);
   }
+  fb_prof_mark(ctx, 4);
   dim3 g2(ctx->B, ctx->n_models);
   gmm_reduce_kernel<<<g2, 128, 0, ctx->stream>>>(ctx->part.p, ctx->row_off.p, ctx->frame_ll.p, ctx->avg_ll.p,
                                                  ctx->n_models, nch, ctx->rows_cap, done_flag);
+  fb_prof_mark(ctx, 5);
   ctx->launches += 2;
   FB_CUDA(cudaGetLastError());
   return FB_OK;

@@ -450,7 +450,9 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
   const int philox = (s->p.rng == FB_RNG_PHILOX);
   int rc;
   dim3 gp(fb_div_up(fb_div_up(s->N, 4), 256), s->pairs_local > 0 ? (s->pairs_local < 8 ? s->pairs_local : 8) : 1);
+  fb_prof_mark(ctx, -1);
   perturb_kernel<<<gp, 256, 0, ctx->stream>>>(d, ctx->wave.p, s->N, philox);
+  fb_prof_mark(ctx, 0);
   ctx->launches += 1;
   if ((rc = fb_run_frontend_flag(ctx, d.flags))) return rc;
   if ((rc = fb_run_gmm_flag(ctx, d.flags))) return rc;
@@ -460,6 +462,7 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
     ctx->launches += 1;
   }
   nes_loss_kernel<<<1, 256, 0, ctx->stream>>>(d, ctx->avg_ll.p, ctx->n_models, mode_get_grad ? 2 : (multi ? 0 : 1));
+  fb_prof_mark(ctx, 6);
   ctx->launches += 1;
   const int nb = fb_div_up(s->N, 128);
   if (!multi) {
@@ -472,6 +475,7 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
     nes_update_kernel<<<nb, 128, 0, ctx->stream>>>(d, 2, 1, 0.0);
     ctx->launches += 3;
   }
+  fb_prof_mark(ctx, 7);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }
@@ -495,7 +499,7 @@ extern "C" int fb_nes_run(fb_ctx *ctx, int n_iters, const double *noise_host) {
       const double *src = noise_host + (size_t)i * per_iter + (size_t)s->pair0 * s->N;
       FB_CUDA(cudaMemcpyAsync(s->noise, src, (size_t)s->pairs_local * s->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (no_graph || host_rng) {
+    if (no_graph || host_rng || ctx->prof_on) {
       if ((rc = nes_enqueue_iteration(ctx, 0))) return rc;
     } else {
       if (!s->graph_exec) {

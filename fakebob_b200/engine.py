@@ -222,6 +222,26 @@ class GmmEngine:
         _lib.check(self.lib.fb_nes_kernel_launches(self.h, C.byref(n)))
         return n.value
 
+    STAGES = ("perturb", "mfcc", "vad_scan", "feats", "gmm", "gmm_reduce", "loss", "update")
+
+    def profile(self, on=True):
+        _lib.check(self.lib.fb_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> {stage: (total_ms, launches)} accumulated since profile(True)."""
+        ms = np.zeros(8, dtype=np.float64)
+        cnt = np.zeros(8, dtype=np.int64)
+        _lib.check(self.lib.fb_profile_read(self.h, _ptr(ms), _ptr(cnt)))
+        return {s: (float(ms[i]), int(cnt[i])) for i, s in enumerate(self.STAGES)}
+
+    def voiced_rows(self):
+        r = C.c_int(0)
+        _lib.check(self.lib.fb_get_voiced_rows(self.h, C.byref(r)))
+        return r.value
+
+    def set_stream(self, cuda_stream_ptr):
+        _lib.check(self.lib.fb_set_stream(self.h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
     def synchronize(self):
         _lib.check(self.lib.fb_synchronize(self.h))
 

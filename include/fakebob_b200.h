@@ -134,6 +134,15 @@ int fb_nes_get_grad(fb_ctx *ctx, const double *noise_host, double *final_loss, d
 int fb_nes_apply_update(fb_ctx *ctx, double lr);
 int fb_nes_kernel_launches(fb_ctx *ctx, int64_t *count);
 
+/* ---- per-stage device timing (CUDA events on the context's stream; disables graph replay while on) ----
+ * Stage ids: 0 perturb, 1 mfcc, 2 vad_scan, 3 feats, 4 gmm, 5 gmm_reduce, 6 loss, 7 update(+collective).
+ * fb_profile_read returns accumulated milliseconds and launch counts per stage since fb_profile_enable(ctx, 1). */
+#define FB_PROF_STAGES 8
+int fb_profile_enable(fb_ctx *ctx, int on);
+int fb_profile_read(fb_ctx *ctx, double *ms_host, int64_t *count_host);
+/* Total voiced rows (frames) of the last scored batch: the GMM kernel's M dimension. */
+int fb_get_voiced_rows(fb_ctx *ctx, int *rows);
+
 /* ---- multi-GPU: one process per GPU, antithetic pairs sharded across ranks ---------------
  * New (nothing in the reference communicates): a single ncclAllReduce(sum, float64) of
  * [grad partial (N) | losses (S+1) | score_0 (K)] per iteration on the context's stream.

@@ -1,0 +1,160 @@
+"""GPU parity tests for the NES attack loop (FakeBob.attack / get_grad / estimate_threshold)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import test_audio as make_audio
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scorers(small_tree):
+    from fakebob_b200.gmm_ubm_CSI import gmm_CSI
+    from fakebob_b200.gmm_ubm_OSI import gmm_OSI
+    from fakebob_b200.gmm_ubm_SV import gmm_SV
+    t = small_tree
+    return {
+        "OSI": gmm_OSI(t["root"] + "/n-osi", t["models"], t["ubm"], pre_model_dir=t["pre_model_dir"]),
+        "CSI": gmm_CSI(t["root"] + "/n-csi", t["models"], pre_model_dir=t["pre_model_dir"]),
+        "SV": gmm_SV(t["root"] + "/n-sv", t["models"][0], t["ubm"], pre_model_dir=t["pre_model_dir"]),
+    }
+
+
+CASES = [
+    ("OSI", "untargeted", dict(threshold=1.0)),
+    ("OSI", "targeted", dict(threshold=0.05, target=2)),
+    ("CSI", "targeted", dict(target=1)),
+    ("CSI", "untargeted", dict(true=0)),
+    ("SV", "untargeted", dict(threshold=1.0)),
+]
+
+
+@pytest.mark.parametrize("task,attack_type,kw", CASES)
+def test_attack_bit_exact_given_same_scores_numpy_rng(scorers, tmp_path, task, attack_type, kw):
+    """Layer (ii) of SURVEY hard-part 3: with the reference's numpy noise stream and the same scorer, the
+    device loop (perturb, int16 quantisation, loss, pairwise-order gradient, momentum, sign step, clip,
+    plateau schedule, early stop) is bit-identical to the CPU restatement of FAKEBOB.py driven by that scorer."""
+    from fakebob_b200.FAKEBOB import FakeBob
+    from oracle.nes import OracleFakeBob
+    model = scorers[task]
+    audio = make_audio(31, 0, n=16000)
+    hp = dict(adver_thresh=0.0, epsilon=0.002, max_iter=12, samples_per_draw=10, plateau_length=3)
+    np.random.seed(99)
+    fb = FakeBob(task, attack_type, model, rng="numpy", verbose=False, **hp)
+    cp = str(tmp_path / "cp.pkl")
+    adv_g, flag_g = fb.attack(audio.copy(), cp, **kw)
+    np.random.seed(99)
+    _ = np.random.randint(0, 2 ** 62)        # FakeBob draws its Philox seed from the global stream at construction
+    ob = OracleFakeBob(task, attack_type, model, **hp)
+    adv_o, flag_o = ob.attack(audio.copy(), None, **kw)
+    assert flag_g == flag_o
+    assert len(ob.log) == fb.iters_done
+    assert np.array_equal(fb.final_adver, ob.final_adver)
+    assert np.array_equal(adv_g, adv_o)
+    for it, row in enumerate(ob.log):
+        assert fb.log[it, 0] == row[0]                       # distance
+        assert fb.log[it, 1] == float(np.asarray(row[1]).reshape(-1)[0])   # adver_loss
+    with open(cp, "rb") as f:
+        rows = pickle.load(f)
+    assert len(rows) == fb.iters_done and len(rows[0]) == 4
+
+
+def test_attack_philox_matches_oracle_philox(scorers):
+    """rng='philox': the device generator and oracle/philox.py produce the same stream (integers exact,
+    Box-Muller within libm ulps), so with the same scorer the trajectories coincide."""
+    from fakebob_b200.FAKEBOB import FakeBob
+    from oracle.nes import OracleFakeBob, PhiloxNoise
+    model = scorers["OSI"]
+    audio = make_audio(32, 1, n=16000)
+    hp = dict(max_iter=10, samples_per_draw=8, plateau_length=3)
+    fb = FakeBob("OSI", "untargeted", model, rng="philox", seed=0x1234ABCD5678, verbose=False, iters_per_launch=4, **hp)
+    adv_g, flag_g = fb.attack(audio.copy(), None, threshold=1.0)
+    ob = OracleFakeBob("OSI", "untargeted", model, noise_fn=PhiloxNoise(0x1234ABCD5678), **hp)
+    adv_o, flag_o = ob.attack(audio.copy(), None, threshold=1.0)
+    assert flag_g == flag_o and fb.iters_done == len(ob.log)
+    agree = np.mean(fb.final_adver == ob.final_adver)
+    assert agree > 0.9999
+    assert np.abs(fb.log[:len(ob.log), 1] - np.array([float(np.asarray(r[1]).reshape(-1)[0]) for r in ob.log])).max() < 1e-6
+
+
+def test_early_stop_and_success_flag(scorers):
+    from fakebob_b200.FAKEBOB import FakeBob
+    model = scorers["SV"]
+    audio = make_audio(33, 0, n=16000)
+    s0 = model.score(audio)
+    fb = FakeBob("SV", "untargeted", model, max_iter=20, samples_per_draw=6, verbose=False, seed=1)
+    adv, flag = fb.attack(audio, None, threshold=float(s0) - 1.0)      # already accepted -> loss < 0 at iter 0
+    assert flag == 1 and fb.iters_done == 1
+    assert adv.shape == (16000, 1) and adv.dtype == np.int16
+    assert np.array_equal(adv[:, 0], (audio * 32768).astype(np.int16))
+    fb2 = FakeBob("SV", "untargeted", model, max_iter=5, samples_per_draw=6, verbose=False, seed=1)
+    adv2, flag2 = fb2.attack(audio, None, threshold=float(s0) + 50.0)  # unreachable
+    assert flag2 == -1 and fb2.iters_done == 5
+    assert np.max(np.abs(fb2.final_adver[:, 0] - audio)) <= 0.002 + 1e-12
+
+
+def test_end_to_end_against_cpu_oracle_scorer(scorers, small_oracle_models):
+    """Layer (iii): GPU attack vs the all-CPU oracle (oracle scorer + oracle NES), same Philox stream.
+    Scores differ at the 1e-4 level so trajectories are compared statistically."""
+    from fakebob_b200.FAKEBOB import FakeBob
+    from oracle.nes import OracleFakeBob, PhiloxNoise
+    from oracle.scorers import OracleGmmSV
+    ubm, spk = small_oracle_models
+    model = scorers["SV"]
+    ref_model = OracleGmmSV(ubm, spk[0])
+    audio = make_audio(34, 2, n=16000)
+    thr = float(model.score(audio)) + 0.08
+    hp = dict(max_iter=8, samples_per_draw=8)
+    fb = FakeBob("SV", "untargeted", model, seed=77, verbose=False, **hp)
+    fb.attack(audio.copy(), None, threshold=thr)
+    ob = OracleFakeBob("SV", "untargeted", ref_model, noise_fn=PhiloxNoise(77), **hp)
+    ob.attack(audio.copy(), None, threshold=thr)
+    n = min(fb.iters_done, len(ob.log))
+    assert abs(fb.iters_done - len(ob.log)) <= 1
+    lg = fb.log[:n, 1]
+    lo = np.array([float(np.asarray(r[1]).reshape(-1)[0]) for r in ob.log[:n]])
+    assert np.abs(lg - lo).max() < 5e-3
+    assert np.mean(np.sign(fb.final_adver - audio[:, None]) == np.sign(ob.final_adver - audio[:, None])) > 0.8
+
+
+def test_get_grad_and_estimate_threshold(scorers):
+    from fakebob_b200.FAKEBOB import FakeBob
+    from oracle.nes import OracleFakeBob
+    model = scorers["OSI"]
+    audio = make_audio(35, 1, n=16000)
+    np.random.seed(5)
+    fb = FakeBob("OSI", "untargeted", model, samples_per_draw=8, rng="numpy", verbose=False)
+    fb.threshold = 0.7
+    fl, g, al, sc = fb.get_grad(audio)
+    np.random.seed(5)
+    _ = np.random.randint(0, 2 ** 62)
+    ob = OracleFakeBob("OSI", "untargeted", model, samples_per_draw=8)
+    ob.threshold = 0.7
+    fl2, g2, al2, sc2 = ob.get_grad(audio)
+    assert fl == fl2 and np.array_equal(g, g2) and al[0] == al2[0] and np.array_equal(sc, sc2)
+    # estimate_threshold: same control flow and result as the restated reference with the same scorer
+    model.threshold = float(np.max(model.score(audio))) + 0.02
+    np.random.seed(6)
+    fb = FakeBob("OSI", "targeted", model, samples_per_draw=8, rng="numpy", verbose=False, max_lr=0.001)
+    r1 = fb.estimate_threshold(audio)
+    np.random.seed(6)
+    _ = np.random.randint(0, 2 ** 62)
+    ob = OracleFakeBob("OSI", "targeted", model, samples_per_draw=8, max_lr=0.001)
+    r2 = ob.estimate_threshold(audio)
+    assert r1[0] == r2[0] and r1[1] == r2[1]
+    assert fb.attack_type == "targeted"
+    model.threshold = 0.0
+
+
+def test_requires_device_backed_model():
+    from fakebob_b200.FAKEBOB import FakeBob
+
+    class Stub:
+        def score(self, a):
+            return 0.0
+
+    with pytest.raises(TypeError):
+        FakeBob("SV", "untargeted", Stub())
