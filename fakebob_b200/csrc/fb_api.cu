@@ -76,7 +76,7 @@ extern "C" int fb_ctx_destroy(fb_ctx *ctx) {
   ctx->w_img.release(); ctx->gconst2.release(); ctx->w_f32.release(); ctx->gconst_nat.release();
   ctx->wave.release(); ctx->wave_off.release(); ctx->frame_off.release(); ctx->mfcc.release();
   ctx->vrank.release(); ctx->nvoiced.release(); ctx->row_off.release(); ctx->misc.release();
-  ctx->a_img.release(); ctx->raw72.release(); ctx->feats_f32.release(); ctx->part.release();
+  ctx->a_img.release(); ctx->raw72.release(); ctx->cmn_prefix.release(); ctx->feats_f32.release(); ctx->part.release();
   ctx->frame_ll.release(); ctx->avg_ll.release();
   if (ctx->tables_dev) cudaFree(ctx->tables_dev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

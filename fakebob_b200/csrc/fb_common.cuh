@@ -15,6 +15,9 @@
 #define FB_NCEPS       24
 #define FB_DIM         72      // 24 x (static, delta, delta-delta)
 #define FB_KSLABS      18      // K = 144 = [x | x^2] in slabs of 8 fp16
+#define FB_A_HI_SLABS  20      // + the "ones" slab (gconst rides in the MMA) + one zero slab
+#define FB_A_TILE_SLABS 38     // hi 20 + lo 18 slabs per 128-row tile
+#define FB_W_HI_SLABS  20      // + gconst slab + zero slab
 #define FB_TILE_M      128
 #define FB_STAGE_N     64      // W columns per smem stage
 #define FB_CHUNK_N     128     // accumulator columns per (tile, unit)
@@ -48,8 +51,8 @@ struct FbTables {
   float2 tw512[FB_FFT_N];                 // exp(-2 pi i q / 512)
   int    mel_start[32];
   int    mel_len[32];
-  float  mel_w[32][FB_MEL_MAXLEN];
-  float  dct[FB_NCEPS][32];               // lifter folded out (applied separately like Kaldi)
+  float  mel_w_t[FB_MEL_MAXLEN][32];      // [bin offset][filter]: lanes (filters) read consecutive words
+  float  dct_t[32][32];                   // [mel bin][cepstrum]; lifter applied separately like Kaldi
   float  lifter[FB_NCEPS];
   float  dscale1[7];                      // delta scales (window 3)
   float  dscale2[13];
@@ -72,7 +75,10 @@ struct DevBuf {
     fb_bump_alloc_epoch();
     size_t cap = want + want / 8 + 64;
     FB_CUDA(cudaMalloc(&p, cap * sizeof(T)));
-    if (zero) FB_CUDA(cudaMemset(p, 0, cap * sizeof(T)));
+    if (zero) {
+      FB_CUDA(cudaMemset(p, 0, cap * sizeof(T)));
+      FB_CUDA(cudaDeviceSynchronize());          // the context's stream is non-blocking w.r.t. the legacy stream
+    }
     n = cap;
     return FB_OK;
   }
@@ -120,8 +126,9 @@ struct fb_ctx {
   DevBuf<int>     nvoiced;     // [B]
   DevBuf<int>     row_off;     // [B+1]
   DevBuf<int>     misc;        // [0]=ticket, [1]=error flag, [2]=M (total voiced rows)
-  DevBuf<__half>  a_img;       // [n_tiles_pad][2][18][128][8]
+  DevBuf<__half>  a_img;       // [n_tiles][hi 19 | lo 18 slabs][128][8]
   DevBuf<float>   raw72;       // global fallback scratch for long utterances
+  DevBuf<double>  cmn_prefix;  // idem (float64 prefix sums)
   DevBuf<float>   feats_f32;   // [rows][72] when debug
   DevBuf<float2>  part;        // [model][C/128][rows_pad] (max, sum) in log2 domain
   DevBuf<float>   frame_ll;    // [model][rows_pad]

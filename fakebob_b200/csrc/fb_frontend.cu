@@ -57,13 +57,13 @@ int fb_prepare_tables(fb_ctx *ctx) {
     t.mel_len[b] = len;
     for (int i = 0; i < len; ++i) {
       float mel = mel_scale_f(fft_bin_width * (first + i));
-      t.mel_w[b][i] = (mel <= center) ? (mel - left) / (center - left) : (right - mel) / (right - center);
+      t.mel_w_t[i][b] = (mel <= center) ? (mel - left) / (center - left) : (right - mel) / (right - center);
     }
   }
   t.num_mel = nb;
   for (int k = 0; k < FB_NCEPS; ++k)
     for (int n = 0; n < nb; ++n)
-      t.dct[k][n] = (k == 0) ? (float)sqrt(1.0 / nb) : (float)(sqrt(2.0 / nb) * cos(M_PI / nb * (n + 0.5) * k));
+      t.dct_t[n][k] = (k == 0) ? (float)sqrt(1.0 / nb) : (float)(sqrt(2.0 / nb) * cos(M_PI / nb * (n + 0.5) * k));
   for (int k = 0; k < FB_NCEPS; ++k) t.lifter[k] = (float)(1.0 + 0.5 * c.cepstral_lifter * sin(M_PI * k / c.cepstral_lifter));
   // delta scales (feature-functions.cc DeltaFeatures ctor), window 3, order 2, float arithmetic
   {
@@ -109,13 +109,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 #define MFCC_WARPS 8
+#define FFT_PAD(i) ((i) + ((i) >> 2))          // float2 index padding: radix-4 Stockham stores become conflict-free
+#define FFT_BUF 320                             // 256 + 64 padding
 
 __global__ void __launch_bounds__(MFCC_WARPS * 32)
 mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_off,
             const int *__restrict__ frame_off, const FbTables *__restrict__ tb,
             float *__restrict__ mfcc, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  __shared__ float2 s_buf[MFCC_WARPS][2][256];
+  __shared__ float2 s_buf[MFCC_WARPS][2][FFT_BUF];
   __shared__ float2 s_tw[FB_FFT_N];
   __shared__ float s_lm[MFCC_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,17 +165,17 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
   e = warp_sum(e);
   const float log_energy = logf(fmaxf(e, 1.1920928955078125e-07f));
   __syncwarp();
-  // ---- pre-emphasis + Povey window, zero-padded to 512 -> bufB (interleaved complex z[n] = x[2n] + i x[2n+1])
+  // ---- pre-emphasis + Povey window, zero-padded to 512 -> bufB as complex z[n] = x[2n] + i x[2n+1] (padded index)
   const float pe = tb->preemph;
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    int i = lane + 32 * q;
+    const int i = lane + 32 * q;
     float v = 0.f;
-    if (i < FB_FRAME_LEN) {
-      float prev = bufA[i > 0 ? i - 1 : 0];
+    if (q < 13 && i < FB_FRAME_LEN) {
+      const float prev = bufA[i > 0 ? i - 1 : 0];
       v = (x[q < 13 ? q : 0] - pe * prev) * __ldg(&tb->window[i]);
     }
-    bufB[i] = v;
+    bufB[2 * FFT_PAD(i >> 1) + (i & 1)] = v;
   }
   __syncwarp();
   // ---- 256-point complex FFT, radix-4 Stockham, stages Ns = 1, 4, 16, 64
@@ -186,8 +188,8 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
     for (int h = 0; h < 2; ++h) {
       const int j = lane + 32 * h;
       const int k = j & (Ns - 1);
-      const int tws = (k << (7 - ls));       // k * (512 / (4*Ns)) in the 512-entry table (= 2 * k*64/Ns)
-      float2 v0 = in[j], v1 = in[j + 64], v2 = in[j + 128], v3 = in[j + 192];
+      const int tws = (k << (7 - ls));       // k * 512 / (4 Ns) in the 512-entry table
+      float2 v0 = in[FFT_PAD(j)], v1 = in[FFT_PAD(j + 64)], v2 = in[FFT_PAD(j + 128)], v3 = in[FFT_PAD(j + 192)];
       if (ls > 0) {
         v1 = cmul(v1, s_tw[tws]);
         v2 = cmul(v2, s_tw[2 * tws]);
@@ -199,10 +201,10 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
       float2 d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
       float2 a3 = make_float2(d13.y, -d13.x);                 // -i * (v1 - v3)
       const int j0 = ((j - k) << 2) + k;
-      out[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-      out[j0 + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-      out[j0 + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-      out[j0 + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+      out[FFT_PAD(j0)] = make_float2(a0.x + a2.x, a0.y + a2.y);
+      out[FFT_PAD(j0 + Ns)] = make_float2(a1.x + a3.x, a1.y + a3.y);
+      out[FFT_PAD(j0 + 2 * Ns)] = make_float2(a0.x - a2.x, a0.y - a2.y);
+      out[FFT_PAD(j0 + 3 * Ns)] = make_float2(a1.x - a3.x, a1.y - a3.y);
     }
     __syncwarp();
     float2 *tmp = in; in = out; out = tmp;
@@ -212,8 +214,8 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const int k = lane + 32 * m;
-    float2 zk = in[k];
-    float2 zc = in[(256 - k) & 255];
+    float2 zk = in[FFT_PAD(k)];
+    float2 zc = in[FFT_PAD((256 - k) & 255)];
     zc.y = -zc.y;
     float2 ev = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
     float2 df = make_float2(zk.x - zc.x, zk.y - zc.y);
@@ -228,7 +230,7 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
   if (lane < tb->num_mel) {
     const int st = tb->mel_start[lane], ln = tb->mel_len[lane];
     float acc = 0.f;
-    for (int i = 0; i < ln; ++i) acc += __ldg(&tb->mel_w[lane][i]) * pw[st + i];
+    for (int i = 0; i < ln; ++i) acc += __ldg(&tb->mel_w_t[i][lane]) * pw[st + i];
     lm = logf(fmaxf(acc, 1.1920928955078125e-07f));
   }
   s_lm[warp][lane] = lm;
@@ -236,7 +238,7 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
   if (lane < FB_NCEPS) {
     float c = 0.f;
     const int nm = tb->num_mel;
-    for (int m = 0; m < nm; ++m) c += __ldg(&tb->dct[lane][m]) * s_lm[warp][m];
+    for (int m = 0; m < nm; ++m) c += __ldg(&tb->dct_t[m][lane]) * s_lm[warp][m];
     c *= __ldg(&tb->lifter[lane]);
     if (lane == 0) c = log_energy;
     mfcc[(int64_t)(f0 + t) * FB_NCEPS + lane] = c;
@@ -340,105 +342,146 @@ vad_scan_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_of
 }
 
 // ------------------------------------------------------------------------------------------------
-// Deltas (order 2, window 3), sliding CMN (centred window, double running sums), voiced-row
-// compaction, per-dimension power-of-two scaling and the fp16 hi/lo split of [x | x^2] written
-// straight into the tensor-core operand image  a_img[tile][hi|lo][slab 18][row 128][8].
-// One CTA per utterance; the (T x 72) delta block lives in shared memory when it fits.
+// Deltas (order 2, window 3), sliding CMN (centred window, float64 prefix sums), voiced-row compaction,
+// per-dimension power-of-two scaling and the fp16 hi/lo split of [x | x^2], written straight into the
+// tensor-core operand image  a_img[tile][hi: 19 slabs | lo: 18 slabs][row 128][8 halfs].
+// One CTA per (utterance, output slab): slab sl = 3*order + cepstra-group holds dims d = 24*order + 8*cg + 0..7,
+// so each CTA owns x-slab sl and x^2-slab 9+sl and every store is a full 16-byte row chunk.
 // ------------------------------------------------------------------------------------------------
-#define FEATS_THREADS 576   // 8 segments x 72 dims
+#define FEATS_THREADS 256
+#define FEATS_NSEG (FEATS_THREADS / 8)
 
-__device__ __forceinline__ void store_split(__half *__restrict__ a_img, int row, int d, float v) {
-  v = fminf(fmaxf(v, -60000.f), 60000.f);
-  const __half hi = __float2half_rn(v);
-  const __half lo = __float2half_rn(v - __half2float(hi));
-  const int tile = row >> 7, rr = row & 127, slab = d >> 3, e = d & 7;
-  const size_t base = ((size_t)tile * 2 * FB_KSLABS + slab) * (FB_TILE_M * 8) + rr * 8 + e;
-  a_img[base] = hi;
-  a_img[base + (size_t)FB_KSLABS * FB_TILE_M * 8] = lo;
+__device__ __forceinline__ void split_pack8(const float *v, uint4 &hi, uint4 &lo) {
+  __half h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float c = fminf(fmaxf(v[i], -60000.f), 60000.f);
+    h[i] = __float2half_rn(c);
+    l[i] = __float2half_rn(c - __half2float(h[i]));
+  }
+  hi = *reinterpret_cast<uint4 *>(h);
+  lo = *reinterpret_cast<uint4 *>(l);
 }
 
 __global__ void __launch_bounds__(FEATS_THREADS)
 feats_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_off, const int *__restrict__ vrank,
              const int *__restrict__ row_off, const FbTables *__restrict__ tb, __half *__restrict__ a_img,
-             float *__restrict__ feats_f32, float *__restrict__ raw_global, int use_smem,
-             const int *__restrict__ done_flag) {
+             float *__restrict__ feats_f32, float *__restrict__ raw_global, double *__restrict__ pre_global,
+             int use_smem, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  extern __shared__ float s_raw[];
-  const int b = blockIdx.x;
+  extern __shared__ double s_dyn[];
+  __shared__ double s_seg[FEATS_NSEG][8];
+  const int sl = blockIdx.x;                  // output slab 0..8
+  const int ord = sl / 3, cg = sl - 3 * ord;
+  const int b = blockIdx.y;
   const int f0 = frame_off[b];
   const int T = frame_off[b + 1] - f0;
-  float *raw = use_smem ? s_raw : (raw_global + (size_t)f0 * FB_DIM);
-  const float *mf = mfcc + (size_t)f0 * FB_NCEPS;
-  // ---- phase A: [static | delta | delta-delta], float accumulation in Kaldi's tap order
-  for (int idx = threadIdx.x; idx < T * FB_DIM; idx += blockDim.x) {
-    const int t = idx / FB_DIM, d = idx - t * FB_DIM;
-    const int k = d / FB_NCEPS, c = d - k * FB_NCEPS;
+  // P[(T+1)][8] float64 prefix sums, raw[T][8] float features of this slab
+  double *P = use_smem ? s_dyn : pre_global + ((size_t)(f0 + b) * 9 + (size_t)sl * (T + 1)) * 8;
+  float *raw = use_smem ? reinterpret_cast<float *>(s_dyn + (size_t)(T + 1) * 8)
+                        : raw_global + ((size_t)f0 * 9 + (size_t)sl * T) * 8;
+  const float *mf = mfcc + (size_t)f0 * FB_NCEPS + cg * 8;
+  // ---- phase A: this slab's static / delta / delta-delta values, float accumulation in Kaldi's tap order
+  float sc1[7], sc2[13];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) sc1[j] = tb->dscale1[j];
+#pragma unroll
+  for (int j = 0; j < 13; ++j) sc2[j] = tb->dscale2[j];
+  for (int idx = threadIdx.x; idx < T * 8; idx += blockDim.x) {
+    const int t = idx >> 3, ci = idx & 7;
     float v;
-    if (k == 0) {
-      v = mf[t * FB_NCEPS + c];
-    } else if (k == 1) {
+    if (ord == 0) {
+      v = mf[t * FB_NCEPS + ci];
+    } else if (ord == 1) {
       v = 0.f;
 #pragma unroll
-      for (int j = -3; j <= 3; ++j) {
-        const float s = tb->dscale1[j + 3];
-        if (s != 0.f) {
-          int tt = min(max(t + j, 0), T - 1);
-          v = __fadd_rn(v, __fmul_rn(s, mf[tt * FB_NCEPS + c]));
-        }
-      }
+      for (int j = -3; j <= 3; ++j)
+        if (sc1[j + 3] != 0.f) v = __fadd_rn(v, __fmul_rn(sc1[j + 3], mf[min(max(t + j, 0), T - 1) * FB_NCEPS + ci]));
     } else {
       v = 0.f;
 #pragma unroll
-      for (int j = -6; j <= 6; ++j) {
-        const float s = tb->dscale2[j + 6];
-        if (s != 0.f) {
-          int tt = min(max(t + j, 0), T - 1);
-          v = __fadd_rn(v, __fmul_rn(s, mf[tt * FB_NCEPS + c]));
-        }
-      }
+      for (int j = -6; j <= 6; ++j)
+        if (sc2[j + 6] != 0.f) v = __fadd_rn(v, __fmul_rn(sc2[j + 6], mf[min(max(t + j, 0), T - 1) * FB_NCEPS + ci]));
     }
     raw[idx] = v;
   }
   __syncthreads();
-  // ---- phase B: sliding-window mean subtraction, running sums in double (SlidingWindowCmn)
-  const int nseg = blockDim.x / FB_DIM;
-  const int g = threadIdx.x / FB_DIM, d = threadIdx.x - g * FB_DIM;
-  if (g >= nseg) return;
-  const int L = (T + nseg - 1) / nseg;
-  const int t0 = g * L, t1 = min(T, t0 + L);
-  const int W = tb->cmn_window;
-  const float scale = tb->feat_scale[d];
-  const int r0 = row_off[b];
-  int pws = -1, pwe = -1;
-  double cur = 0.0;
+  // ---- phase B: float64 exclusive prefix sums over frames (segment sums -> scan of segments -> local prefixes)
+  const int ci = threadIdx.x & 7, g = threadIdx.x >> 3;
+  const int L = (T + FEATS_NSEG - 1) / FEATS_NSEG;
+  const int t0 = min(g * L, T), t1 = min(t0 + L, T);
+  double acc = 0.0;
+  for (int t = t0; t < t1; ++t) acc = __dadd_rn(acc, (double)raw[t * 8 + ci]);
+  s_seg[g][ci] = acc;
+  __syncthreads();
+  double run = 0.0;
+  for (int q = 0; q < g; ++q) run = __dadd_rn(run, s_seg[q][ci]);
   for (int t = t0; t < t1; ++t) {
+    P[t * 8 + ci] = run;
+    run = __dadd_rn(run, (double)raw[t * 8 + ci]);
+  }
+  if (t1 == T && t0 < T) P[T * 8 + ci] = run;
+  if (T == 0) return;
+  __syncthreads();
+  // ---- phase C: x - window mean, scale, split, pack; one thread per voiced frame (8 dims = one 16-byte chunk)
+  const int W = tb->cmn_window;
+  const int r0 = row_off[b];
+  float scale[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) scale[i] = tb->feat_scale[ord * FB_NCEPS + cg * 8 + i];
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int r = vrank[f0 + t];
+    if (r < 0) continue;
     int ws = t - W / 2, we = ws + W;
     if (ws < 0) { we -= ws; ws = 0; }
     if (we > T) { ws -= (we - T); we = T; if (ws < 0) ws = 0; }
-    if (pws < 0) {
-      cur = 0.0;
-      for (int u = ws; u < we; ++u) cur = __dadd_rn(cur, (double)raw[u * FB_DIM + d]);
-    } else {
-      if (ws > pws) cur = __dadd_rn(cur, -(double)raw[pws * FB_DIM + d]);
-      if (we > pwe) cur = __dadd_rn(cur, (double)raw[pwe * FB_DIM + d]);
+    const float alpha = __fdiv_rn(-1.0f, (float)(we - ws));
+    float xs[8], x2[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double cur = __dadd_rn(P[we * 8 + i], -P[ws * 8 + i]);
+      o[i] = (float)__dadd_rn((double)raw[t * 8 + i], __dmul_rn((double)alpha, cur));
+      xs[i] = o[i] * scale[i];                 // exact: power-of-two scale
+      x2[i] = xs[i] * xs[i];
     }
-    pws = ws; pwe = we;
-    const int r = vrank[f0 + t];
-    if (r >= 0) {
-      const float alpha = __fdiv_rn(-1.0f, (float)(we - ws));
-      const float o = (float)__dadd_rn((double)raw[t * FB_DIM + d], __dmul_rn((double)alpha, cur));
-      const int row = r0 + r;
-      if (feats_f32) feats_f32[(size_t)row * FB_DIM + d] = o;
-      const float xs = o * scale;                 // exact: scale is a power of two
-      store_split(a_img, row, d, xs);
-      store_split(a_img, row, FB_DIM + d, xs * xs);
+    const int row = r0 + r;
+    if (feats_f32) {
+      float4 *dst = reinterpret_cast<float4 *>(feats_f32 + (size_t)row * FB_DIM + ord * FB_NCEPS + cg * 8);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
+    const int tile = row >> 7, rr = row & 127;
+    uint4 hi, lo;
+    __half *tbase = a_img + (size_t)tile * FB_A_TILE_SLABS * (FB_TILE_M * 8) + rr * 8;
+    split_pack8(xs, hi, lo);
+    *reinterpret_cast<uint4 *>(tbase + (size_t)sl * (FB_TILE_M * 8)) = hi;
+    *reinterpret_cast<uint4 *>(tbase + (size_t)(FB_A_HI_SLABS + sl) * (FB_TILE_M * 8)) = lo;
+    split_pack8(x2, hi, lo);
+    *reinterpret_cast<uint4 *>(tbase + (size_t)(9 + sl) * (FB_TILE_M * 8)) = hi;
+    *reinterpret_cast<uint4 *>(tbase + (size_t)(FB_A_HI_SLABS + 9 + sl) * (FB_TILE_M * 8)) = lo;
   }
+}
+
+// The "ones" slab (hi slab 18) of every tile: columns 0..2 = 1.0 so the three fp16 terms of gconst in W add up in the MMA.
+__global__ void a_img_init_kernel(__half *a_img, int n_tiles) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tiles * FB_TILE_M) return;
+  const int tile = idx / FB_TILE_M, rr = idx - tile * FB_TILE_M;
+  __half *p = a_img + ((size_t)tile * FB_A_TILE_SLABS + FB_KSLABS) * (FB_TILE_M * 8) + rr * 8;
+  const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+  p[0] = one; p[1] = one; p[2] = one;
+#pragma unroll
+  for (int i = 3; i < 8; ++i) p[i] = zero;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Host: batch reservation and launch sequence
 // ------------------------------------------------------------------------------------------------
+#define FB_FEATS_SMEM_MAX (200 * 1024)
+static size_t fb_feats_smem_bytes(int max_frames) {
+  return (size_t)(max_frames + 1) * 8 * sizeof(double) + (size_t)max_frames * 8 * sizeof(float);
+}
+
 int fb_reserve_batch(fb_ctx *ctx, int B, const int64_t *offsets_host) {
   FB_CHECK_ARG(B > 0, "B must be positive");
   FB_CHECK_ARG(offsets_host != nullptr, "offsets is NULL");
@@ -472,7 +515,10 @@ int fb_reserve_batch(fb_ctx *ctx, int B, const int64_t *offsets_host) {
     const int cap = rows_pad + rows_pad / 8;
     const int cap_pad = ((cap + 255) / 256) * 256;
     ctx->a_img.release();
-    if ((rc = ctx->a_img.ensure((size_t)cap_pad * 2 * FB_KSLABS * 8, true))) return rc;
+    const int n_tiles = cap_pad / FB_TILE_M;
+    if ((rc = ctx->a_img.ensure((size_t)n_tiles * FB_A_TILE_SLABS * FB_TILE_M * 8, true))) return rc;
+    a_img_init_kernel<<<fb_div_up((int64_t)n_tiles * FB_TILE_M, 256), 256, 0, ctx->stream>>>(ctx->a_img.p, n_tiles);
+    FB_CUDA(cudaGetLastError());
     ctx->rows_cap = cap_pad;
     ctx->part.release();
     ctx->frame_ll.release();
@@ -485,8 +531,10 @@ int fb_reserve_batch(fb_ctx *ctx, int B, const int64_t *offsets_host) {
   }
   if (ctx->debug_feats)
     if ((rc = ctx->feats_f32.ensure((size_t)total_frames * FB_DIM))) return rc;
-  if ((size_t)max_frames * FB_DIM * sizeof(float) > 200 * 1024)
+  if (fb_feats_smem_bytes(max_frames) > FB_FEATS_SMEM_MAX) {
     if ((rc = ctx->raw72.ensure((size_t)total_frames * FB_DIM))) return rc;
+    if ((rc = ctx->cmn_prefix.ensure((size_t)(total_frames + B) * FB_DIM))) return rc;
+  }
   FB_CUDA(cudaMemcpyAsync(ctx->wave_off.p, ctx->off_host.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
   FB_CUDA(cudaMemcpyAsync(ctx->frame_off.p, ctx->frame_off_host.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   return FB_OK;
@@ -503,16 +551,17 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   vad_scan_kernel<<<B, 256, 0, ctx->stream>>>(ctx->mfcc.p, ctx->frame_off.p, ctx->tables_dev, ctx->vrank.p,
                                               ctx->nvoiced.p, ctx->row_off.p, ctx->misc.p, B, done_flag);
   fb_prof_mark(ctx, 2);
-  const size_t smem = (size_t)ctx->max_frames * FB_DIM * sizeof(float);
-  const int use_smem = smem <= 200 * 1024;
-  static size_t configured = 0;
-  if (use_smem && smem > configured) {
-    FB_CUDA(cudaFuncSetAttribute(feats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+  const size_t smem = fb_feats_smem_bytes(ctx->max_frames);
+  const int use_smem = smem <= FB_FEATS_SMEM_MAX;
+  static bool configured = false;
+  if (!configured) {
+    FB_CUDA(cudaFuncSetAttribute(feats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_FEATS_SMEM_MAX));
+    configured = true;
   }
-  feats_kernel<<<B, FEATS_THREADS, use_smem ? smem : 0, ctx->stream>>>(
+  feats_kernel<<<dim3(9, B), FEATS_THREADS, use_smem ? smem : 0, ctx->stream>>>(
       ctx->mfcc.p, ctx->frame_off.p, ctx->vrank.p, ctx->row_off.p, ctx->tables_dev, ctx->a_img.p,
-      ctx->debug_feats ? ctx->feats_f32.p : nullptr, use_smem ? nullptr : ctx->raw72.p, use_smem, done_flag);
+      ctx->debug_feats ? ctx->feats_f32.p : nullptr, use_smem ? nullptr : ctx->raw72.p,
+      use_smem ? nullptr : ctx->cmn_prefix.p, use_smem, done_flag);
   fb_prof_mark(ctx, 3);
   ctx->launches += 3;
   FB_CUDA(cudaGetLastError());

@@ -11,32 +11,49 @@
 // which keeps ~22 significant bits per operand (fp32 Kaldi keeps 24).  W is pre-multiplied by
 // log2(e) so the epilogue works in the log2 domain with ex2.approx.
 //
-// Kernel shape (cta_group::1, persistent, 1 CTA / SM, 192 threads):
-//   warp 0   bulk-copy (TMA engine, cp.async.bulk) producer: A super-tile (2 x 128 rows, hi+lo,
-//            144 KB, resident for all models/columns it is used with) and W stages (64 columns,
-//            hi+lo, 36 KB, 2-deep ring).  Operand images are stored in global memory already in
-//            the UMMA canonical no-swizzle K-major core-matrix order, so every copy is one
-//            contiguous bulk transfer.
-//   warp 1   single-thread tcgen05.mma issuer: per stage 2 tiles x 3 parts x 9 k-blocks of
-//            M128 N64 K16, accumulators double-buffered in TMEM (2 x [2 tiles x 128 cols]).
-//   warps 2-5 epilogue: tcgen05.ld 32x32b.x32, + gconst, online max / sum of ex2 with Kaldi's
-//            log(FLT_EPSILON) pruning, one (max,sum) partial per row per 128-column unit.
+// Kernel shape (cta_group::1, persistent, 1 CTA / SM, 320 threads).  Measured on B200 (profiles/r01_*): with both
+// operands in shared memory the N=64 MMAs need 192 B/clk of smem reads and run at ~68 clk instead of 32, and they starve
+// the bulk-copy writes, so the A operand lives in TENSOR MEMORY instead:
+//   warp 0   bulk-copy (TMA engine, cp.async.bulk) producer into a 5-slot x 40 KB ring: per 256-row super-tile four
+//            A entries (tile0 hi, tile0 lo, tile1 hi, tile1 lo), then per 128-column unit two W stages (64 columns,
+//            hi+lo).  Operand images are stored in global memory already in the UMMA canonical no-swizzle K-major
+//            core-matrix order, so every copy is one contiguous transfer.
+//   warp 1   single thread: tcgen05.cp moves A entries smem -> TMEM (304 columns: 2 tiles x (hi 80 + lo 72)), then per W
+//            stage and tile 28 tcgen05.mma M128 N64 K16 with A from TMEM and B from the ring slot; the two tiles'
+//            accumulators (64 TMEM columns each) ping-pong against the epilogue.
+//   warps 2-9 epilogue (4 per tile, TMEM lane quadrant = warp % 4): tcgen05.ld 32x32b.x32, online max / sum of ex2 with
+//            Kaldi's log(FLT_EPSILON) pruning; gconst is already inside the accumulator (extra k-block of the hi.hi
+//            part: "ones" columns of A times [g_hi g_mid g_lo] rows of W); one (max,sum) partial per row per unit.
 // Work unit = (super-tile, model, 128-column chunk); units are split evenly over the CTAs.
 #include "fb_common.cuh"
 #include <math.h>
 
-#define GMM_THREADS 192
-static constexpr uint32_t kAHalfBytes = FB_KSLABS * FB_TILE_M * 16;           // 36864: one of hi/lo of one tile
-static constexpr uint32_t kATileBytes = 2 * kAHalfBytes;                      // 73728
-static constexpr uint32_t kASuperBytes = 2 * kATileBytes;                     // 147456
-static constexpr uint32_t kWHalfBytes = FB_KSLABS * FB_STAGE_N * 16;          // 18432
-static constexpr uint32_t kWStageBytes = 2 * kWHalfBytes;                     // 36864
-static constexpr uint32_t kNumWStages = 2;
-static constexpr uint32_t kSmemA = 0;
-static constexpr uint32_t kSmemW = kASuperBytes;
-static constexpr uint32_t kSmemBar = kSmemW + kNumWStages * kWStageBytes;     // 221184
-static constexpr uint32_t kSmemTotal = kSmemBar + 128;
-static constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;                    // alignment slack
+#ifndef GMM_PARTS
+#define GMM_PARTS 3
+#endif
+#define GMM_THREADS 320                       // producer warp + MMA warp + 8 epilogue warps
+// A image per 128-row tile: hi = 20 slabs (9 x, 9 x^2, 1 "ones" slab carrying the gconst columns, 1 zero slab), lo = 18 slabs.
+// W image per 64-column stage: hi = 20 slabs (18 + gconst slab [g_hi g_mid g_lo 0..] + zero slab), lo = 18 slabs.
+static constexpr uint32_t kSlabA = FB_TILE_M * 16;                             // 2048 B
+static constexpr uint32_t kSlabW = FB_STAGE_N * 16;                            // 1024 B
+static constexpr uint32_t kAHiBytes = FB_A_HI_SLABS * kSlabA;                  // 40960
+static constexpr uint32_t kALoBytes = FB_KSLABS * kSlabA;                      // 36864
+static constexpr uint32_t kATileBytes = kAHiBytes + kALoBytes;                 // 77824
+static constexpr uint32_t kWHiBytes = FB_W_HI_SLABS * kSlabW;                  // 20480
+static constexpr uint32_t kWLoBytes = FB_KSLABS * kSlabW;                      // 18432
+static constexpr uint32_t kWStageBytes = kWHiBytes + kWLoBytes;                // 38912
+static constexpr uint32_t kSlotBytes = 40960;
+static constexpr uint32_t kNumSlots = 5;
+static constexpr uint32_t kSmemBar = kNumSlots * kSlotBytes;                   // 204800
+static constexpr uint32_t kSmemTotal = kSmemBar + 256;
+static constexpr uint32_t kSmemLaunch = kSmemTotal + 128;                      // 128 B alignment slack
+static_assert(kAHiBytes <= kSlotBytes && kWStageBytes <= kSlotBytes, "ring slot too small");
+static_assert(kSmemLaunch <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+// TMEM columns: accumulators [0,128) (tile0 | tile1, 64 each); A operand: tile t hi at 128 + 152 t, lo 80 columns later
+static constexpr uint32_t kTmemAcc = 0;
+static constexpr uint32_t kTmemA = 128;
+static constexpr uint32_t kTmemAHiCols = FB_A_HI_SLABS * 4;                    // 80
+static constexpr uint32_t kTmemATileCols = kTmemAHiCols + FB_KSLABS * 4;       // 152
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,6 +95,18 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// smem (matrix descriptor: 128 rows x 32 bytes = one K=16 fp16 block) -> TMEM lanes 0..127, 8 columns
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t taddr, uint64_t s_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(s_desc) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
   uint32_t *r = reinterpret_cast<uint32_t *>(v);
   asm volatile(
@@ -97,6 +126,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// One lane of a converged warp; lets the compiler treat the guarded region as single-threaded (uniform registers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+
 // K-major, no-swizzle canonical layout: core matrix = 8 rows x 16 bytes (contiguous 128 B);
 // LBO = byte distance between core matrices adjacent in K, SBO = between 8-row groups in M/N.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -112,26 +158,50 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 static constexpr uint32_t kIdesc = (1u << 4) | ((FB_STAGE_N >> 3) << 17) | ((FB_TILE_M >> 4) << 24);
 
 struct GmmArgs {
-  const __half *a_img;      // [super-tile][tile 2][hl 2][18][128][8]
-  const __half *w_img;      // [model][C/64][hl 2][18][64][8]
-  const float *gconst2;     // [model][C]
+  const __half *a_img;      // [tile][hi 19 slabs | lo 18 slabs][128][8]
+  const __half *w_img;      // [model][C/64][hi 20 slabs | lo 18 slabs][64][8]
   float2 *part;             // [model][C/128][rows_cap]
   const int *misc;          // misc[2] = total voiced rows
   const int *done_flag;
   int n_models, C, rows_cap;
 };
 
+// One 32-column group of one accumulator row: online max / sum of 2^(v - max) with Kaldi's cutoff.
+__device__ __forceinline__ void lse_group(const float *v, float &m, float &s) {
+  float c0 = max3(v[0], v[1], v[2]), c1 = max3(v[3], v[4], v[5]);
+#pragma unroll
+  for (int i = 6; i < 30; i += 6) {
+    c0 = max3(c0, v[i], v[i + 1]);
+    c0 = fmaxf(c0, v[i + 2]);
+    c1 = max3(c1, v[i + 3], v[i + 4]);
+    c1 = fmaxf(c1, v[i + 5]);
+  }
+  const float cmax = max3(c0, c1, fmaxf(v[30], v[31]));
+  if (cmax > m) {
+    s *= ex2_approx(m - cmax);
+    m = cmax;
+  }
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float t0 = v[i] - m, t1 = v[i + 1] - m;
+    const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+    if (t0 >= -23.0f) s0 += e0;                 // Kaldi LogSumExp cutoff log(FLT_EPSILON) = -23 in log2
+    if (t1 >= -23.0f) s1 += e1;
+  }
+  s += s0 + s1;
+}
+
 __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   if (g.done_flag && *g.done_flag) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t base = (raw_addr + 127u) & ~127u;
   uint8_t *smem = smem_raw + (base - raw_addr);
   const uint32_t bar0 = base + kSmemBar;
-  const uint32_t bar_a_full = bar0, bar_a_empty = bar0 + 8;
-  const uint32_t bar_w_full = bar0 + 16, bar_w_empty = bar0 + 32;       // [2] each
-  const uint32_t bar_acc_full = bar0 + 48, bar_acc_empty = bar0 + 64;   // [2] each
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmemBar + 96);
+  const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kNumSlots;           // ring slots
+  const uint32_t bar_acc_full = bar0 + 16 * kNumSlots, bar_acc_empty = bar_acc_full + 16;   // [2 tiles] each
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmemBar + 16 * kNumSlots + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.misc[2];
@@ -142,13 +212,13 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   const int u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
 
   if (warp == 0 && lane == 0) {
-    mbar_init(bar_a_full, 1);
-    mbar_init(bar_a_empty, 1);
+    for (uint32_t i = 0; i < kNumSlots; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_w_full + 8 * i, 1);
-      mbar_init(bar_w_empty + 8 * i, 1);
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 4);     // one arrive per epilogue warp
+      mbar_init(bar_acc_empty + 8 * i, 4);     // one arrive per epilogue warp of that tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -163,133 +233,134 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= producer =================
-    if (lane == 0) {
-      int cur_super = -1;
-      uint32_t a_cnt = 0, w_cnt = 0;
-      for (int u = u0; u < u1; ++u) {
-        const int ch = u % nch;
-        const int item = u / nch;
-        const int model = item % g.n_models;
-        const int sp = item / g.n_models;
-        if (sp != cur_super) {
-          if (a_cnt > 0) mbar_wait(bar_a_empty, (a_cnt - 1) & 1);
-          mbar_expect_tx(bar_a_full, kASuperBytes);
-          const uint8_t *src = reinterpret_cast<const uint8_t *>(g.a_img) + (size_t)sp * kASuperBytes;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            bulk_g2s(base + kSmemA + q * kAHalfBytes, src + (size_t)q * kAHalfBytes, kAHalfBytes, bar_a_full);
-          ++a_cnt;
-          cur_super = sp;
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t s = w_cnt & 1;
-          mbar_wait(bar_w_empty + 8 * s, ((w_cnt >> 1) & 1) ^ 1);
-          mbar_expect_tx(bar_w_full + 8 * s, kWStageBytes);
-          const size_t stage_idx = (size_t)model * (g.C / FB_STAGE_N) + (size_t)ch * 2 + h;
-          const uint8_t *src = reinterpret_cast<const uint8_t *>(g.w_img) + stage_idx * kWStageBytes;
-          bulk_g2s(base + kSmemW + s * kWStageBytes, src, kWHalfBytes, bar_w_full + 8 * s);
-          bulk_g2s(base + kSmemW + s * kWStageBytes + kWHalfBytes, src + kWHalfBytes, kWHalfBytes, bar_w_full + 8 * s);
-          ++w_cnt;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      int cur_super = -1;
-      uint32_t a_cnt = 0, w_cnt = 0, acc_cnt = 0;
-      for (int u = u0; u < u1; ++u) {
-        const int item = u / nch;
-        const int sp = item / g.n_models;
-        if (sp != cur_super) {
-          mbar_wait(bar_a_full, a_cnt & 1);
-          ++a_cnt;
-          cur_super = sp;
-        }
-        const uint32_t buf = acc_cnt & 1;
-        mbar_wait(bar_acc_empty + 8 * buf, ((acc_cnt >> 1) & 1) ^ 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t s = w_cnt & 1;
-          mbar_wait(bar_w_full + 8 * s, (w_cnt >> 1) & 1);
-          tc_fence_after();
-          const uint32_t w_hi = base + kSmemW + s * kWStageBytes;
-          const uint32_t w_lo = w_hi + kWHalfBytes;
-#pragma unroll
-          for (int tile = 0; tile < 2; ++tile) {
-            const uint32_t a_hi = base + kSmemA + tile * kATileBytes;
-            const uint32_t a_lo = a_hi + kAHalfBytes;
-            const uint32_t d_tmem = tmem_base + buf * 256 + tile * FB_CHUNK_N + h * FB_STAGE_N;
-#pragma unroll
-            for (int part = 0; part < 3; ++part) {
-              const uint32_t a_base = (part == 1) ? a_lo : a_hi;
-              const uint32_t b_base = (part == 2) ? w_lo : w_hi;
-#pragma unroll
-              for (int kb = 0; kb < FB_KSLABS / 2; ++kb) {
-                const uint64_t ad = make_desc(a_base + kb * 2 * (FB_TILE_M * 16), FB_TILE_M * 16, 128);
-                const uint64_t bd = make_desc(b_base + kb * 2 * (FB_STAGE_N * 16), FB_STAGE_N * 16, 128);
-                tc_mma_f16(d_tmem, ad, bd, kIdesc, (part | kb) ? 1u : 0u);
-              }
-            }
-          }
-          tc_commit(bar_w_empty + 8 * s);
-          ++w_cnt;
-        }
-        tc_commit(bar_acc_full + 8 * buf);
-        ++acc_cnt;
-        const bool last_of_super = (u + 1 == u1) || ((u + 1) / nch / g.n_models != sp);
-        if (last_of_super) tc_commit(bar_a_empty);
-      }
-    }
-  } else {
-    // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
-    const int quad = warp & 3;
-    uint32_t acc_cnt = 0;
+    // ================= producer: ring of kNumSlots slots (whole warp loops, one elected lane issues) =================
+    int cur_super = -1;
+    uint32_t cnt = 0;
     for (int u = u0; u < u1; ++u) {
       const int ch = u % nch;
       const int item = u / nch;
       const int model = item % g.n_models;
       const int sp = item / g.n_models;
-      const uint32_t buf = acc_cnt & 1;
-      mbar_wait(bar_acc_full + 8 * buf, (acc_cnt >> 1) & 1);
-      tc_fence_after();
-      const float *gc = g.gconst2 + (size_t)model * g.C + ch * FB_CHUNK_N;
+      if (sp != cur_super) {
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(g.a_img) + (size_t)sp * 2 * kATileBytes;
 #pragma unroll 1
-      for (int tile = 0; tile < 2; ++tile) {
-        float m = -INFINITY, s = 0.f;
-#pragma unroll 1
-        for (int c8 = 0; c8 < 4; ++c8) {
-          float v[32];
-          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + tile * FB_CHUNK_N + c8 * 32, v);
-          tc_wait_ld();
-          float cmax = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 gq = __ldg(reinterpret_cast<const float4 *>(gc + c8 * 32 + i));
-            v[i] += gq.x; v[i + 1] += gq.y; v[i + 2] += gq.z; v[i + 3] += gq.w;
-            cmax = fmaxf(cmax, fmaxf(fmaxf(v[i], v[i + 1]), fmaxf(v[i + 2], v[i + 3])));
+        for (int e = 0; e < 4; ++e) {          // tile0 hi, tile0 lo, tile1 hi, tile1 lo
+          const uint32_t slot = cnt % kNumSlots;
+          mbar_wait(bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+          if (elect_one()) {
+            const uint32_t bytes = (e & 1) ? kALoBytes : kAHiBytes;
+            mbar_expect_tx(bar_full + 8 * slot, bytes);
+            bulk_g2s(base + slot * kSlotBytes, src + (size_t)(e >> 1) * kATileBytes + ((e & 1) ? kAHiBytes : 0), bytes,
+                     bar_full + 8 * slot);
           }
-          if (cmax > m) {
-            s *= ex2_approx(m - cmax);
-            m = cmax;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float t = v[i] - m;
-            const float e = ex2_approx(t);
-            s += (t >= -23.0f) ? e : 0.f;          // Kaldi LogSumExp cutoff log(FLT_EPSILON) = -23 in log2
-          }
+          __syncwarp();
+          ++cnt;
         }
-        const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
-        g.part[((size_t)model * nch + ch) * g.rows_cap + row] = make_float2(m, s);
+        cur_super = sp;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
-      ++acc_cnt;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t slot = cnt % kNumSlots;
+        mbar_wait(bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar_full + 8 * slot, kWStageBytes);
+          const size_t stage_idx = (size_t)model * (g.C / FB_STAGE_N) + (size_t)ch * 2 + h;
+          bulk_g2s(base + slot * kSlotBytes, reinterpret_cast<const uint8_t *>(g.w_img) + stage_idx * kWStageBytes,
+                   kWStageBytes, bar_full + 8 * slot);
+        }
+        __syncwarp();
+        ++cnt;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== tcgen05 issuer (whole warp loops and waits; one elected lane issues copies / MMAs / commits) =====
+    // smem descriptor with LBO / SBO / version bits and a zero start address; only the 14-bit address field varies
+    const uint64_t desc_w = make_desc(0, kSlabW, 128);
+    const uint64_t desc_a = make_desc(0, kSlabA, 128);
+    int cur_super = -1;
+    uint32_t cnt = 0, sub0 = 0, sub1 = 0;
+    for (int u = u0; u < u1; ++u) {
+      const int item = u / nch;
+      const int sp = item / g.n_models;
+      if (sp != cur_super) {
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t slot = cnt % kNumSlots;
+          mbar_wait(bar_full + 8 * slot, (cnt / kNumSlots) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t src = desc_a + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
+            const uint32_t dst = tmem_base + kTmemA + (e >> 1) * kTmemATileCols + ((e & 1) ? kTmemAHiCols : 0);
+            const int nkb = (e & 1) ? FB_KSLABS / 2 : FB_A_HI_SLABS / 2;
+            for (int kb = 0; kb < nkb; ++kb) tc_cp_128x256b(dst + kb * 8, src + (uint64_t)(kb * ((2 * kSlabA) >> 4)));
+            tc_commit(bar_empty + 8 * slot);
+          }
+          __syncwarp();
+          ++cnt;
+        }
+        cur_super = sp;
+      }
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t slot = cnt % kNumSlots;
+        mbar_wait(bar_full + 8 * slot, (cnt / kNumSlots) & 1);
+        const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
+        const uint64_t w_lo = w_hi + (uint64_t)(kWHiBytes >> 4);
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+          mbar_wait(bar_acc_empty + 8 * tile, ((tile ? sub1 : sub0) & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols;
+            const uint32_t a_lo = a_hi + kTmemAHiCols;
+            const uint32_t d_tmem = tmem_base + kTmemAcc + tile * FB_STAGE_N;
+#pragma unroll
+            for (int part = 0; part < GMM_PARTS; ++part) {
+              const uint32_t a_base = (part == 1) ? a_lo : a_hi;
+              const uint64_t b_base = (part == 2) ? w_lo : w_hi;
+              const int nkb = (part == 0) ? FB_A_HI_SLABS / 2 : FB_KSLABS / 2;      // part 0 carries the gconst k-block
+#pragma unroll
+              for (int kb = 0; kb < nkb; ++kb)
+                tc_mma_f16_ta(d_tmem, a_base + kb * 8, b_base + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
+            }
+            tc_commit(bar_acc_full + 8 * tile);
+            if (tile == 1) tc_commit(bar_empty + 8 * slot);
+          }
+          __syncwarp();
+          if (tile) ++sub1; else ++sub0;
+        }
+        ++cnt;
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, tile = (warp - 2) / 4 =====
+    const int quad = warp & 3;
+    const int tile = (warp - 2) >> 2;
+    uint32_t sub = 0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc + tile * FB_STAGE_N;
+    for (int u = u0; u < u1; ++u) {
+      const int ch = u % nch;
+      const int item = u / nch;
+      const int model = item % g.n_models;
+      const int sp = item / g.n_models;
+      float m = -INFINITY, s = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(bar_acc_full + 8 * tile, sub & 1);
+        tc_fence_after();
+        float va[32], vb[32];
+        tc_ld32(taddr, va);
+        tc_ld32(taddr + 32, vb);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * tile);     // accumulator is in registers: MMA may overwrite
+        ++sub;
+        lse_group(va, m, s);
+        lse_group(vb, m, s);
+      }
+      const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
+      g.part[((size_t)model * nch + ch) * g.rows_cap + row] = make_float2(m, s);
     }
   }
   tc_fence_before();
@@ -320,8 +391,8 @@ gmm_simt_kernel(const __half *__restrict__ a_img, const float *__restrict__ w_f3
     const int r = idx / (2 * FB_DIM), k = idx % (2 * FB_DIM);
     const int row = row0 + r;
     const int tile = row >> 7, rr = row & 127, slab = k >> 3, e = k & 7;
-    const size_t b = ((size_t)tile * 2 * FB_KSLABS + slab) * (FB_TILE_M * 8) + rr * 8 + e;
-    float v = __half2float(a_img[b]) + __half2float(a_img[b + (size_t)FB_KSLABS * FB_TILE_M * 8]);
+    const size_t b = ((size_t)tile * FB_A_TILE_SLABS + slab) * (FB_TILE_M * 8) + rr * 8 + e;
+    float v = __half2float(a_img[b]) + __half2float(a_img[b + (size_t)FB_A_HI_SLABS * FB_TILE_M * 8]);
     const int d = (k < FB_DIM) ? k : k - FB_DIM;
     const float sc = feat_scale[d];
     v = (k < FB_DIM) ? v / sc : v / (sc * sc);
@@ -432,8 +503,9 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
   }
   ctx->tables_dirty = true;
   const int n_stage = C / FB_STAGE_N;
-  const size_t img_halfs = (size_t)n_models * n_stage * 2 * FB_KSLABS * FB_STAGE_N * 8;
-  std::vector<__half> img(img_halfs);
+  const size_t stage_halfs = (size_t)(FB_W_HI_SLABS + FB_KSLABS) * FB_STAGE_N * 8;
+  const size_t img_halfs = (size_t)n_models * n_stage * stage_halfs;
+  std::vector<__half> img(img_halfs, __float2half_rn(0.f));
   std::vector<float> gc2((size_t)n_models * C), gcn((size_t)n_models * C), wf((size_t)n_models * C * 2 * FB_DIM);
   const double log2e = 1.4426950408889634;
   for (int m = 0; m < n_models; ++m) {
@@ -442,6 +514,19 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
       gc2[(size_t)m * C + c] = (float)((double)h.gconsts[c] * log2e);
       gcn[(size_t)m * C + c] = h.gconsts[c];
       const int st = c / FB_STAGE_N, cc = c % FB_STAGE_N;
+      const size_t stage_base = ((size_t)m * n_stage + st) * stage_halfs;
+      {
+        // gconst * log2(e) as three fp16 terms in the extra hi slab (multiplied by the ones slab of A)
+        double gv = (double)h.gconsts[c] * log2e;
+        if (!(gv > -60000.0)) gv = -60000.0;         // zero-weight components: exp2 underflows to 0 anyway
+        if (gv > 60000.0) gv = 60000.0;
+        const __half g0 = __float2half_rn((float)gv);
+        const double r1 = gv - (double)__half2float(g0);
+        const __half g1 = __float2half_rn((float)r1);
+        const __half g2 = __float2half_rn((float)(r1 - (double)__half2float(g1)));
+        const size_t gb = stage_base + (size_t)FB_KSLABS * (FB_STAGE_N * 8) + cc * 8;
+        img[gb] = g0; img[gb + 1] = g1; img[gb + 2] = g2;
+      }
       for (int k = 0; k < 2 * FB_DIM; ++k) {
         const int d = (k < FB_DIM) ? k : k - FB_DIM;
         const double s = ctx->tables_host.feat_scale[d];
@@ -456,9 +541,9 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
         const __half hi = __float2half_rn((float)w);
         const __half lo = __float2half_rn((float)(w - (double)__half2float(hi)));
         const int slab = k >> 3, e = k & 7;
-        const size_t b = ((((size_t)m * n_stage + st) * 2 + 0) * FB_KSLABS + slab) * (FB_STAGE_N * 8) + cc * 8 + e;
+        const size_t b = stage_base + (size_t)slab * (FB_STAGE_N * 8) + cc * 8 + e;
         img[b] = hi;
-        img[b + (size_t)FB_KSLABS * FB_STAGE_N * 8] = lo;
+        img[b + (size_t)FB_W_HI_SLABS * FB_STAGE_N * 8] = lo;
       }
     }
   }
@@ -492,7 +577,6 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     GmmArgs a;
     a.a_img = ctx->a_img.p;
     a.w_img = ctx->w_img.p;
-    a.gconst2 = ctx->gconst2.p;
     a.part = ctx->part.p;
     a.misc = ctx->misc.p;
     a.done_flag = done_flag;
