@@ -252,7 +252,6 @@ def main():
         torch.cuda.synchronize()
         barrier()
         ms_hot = e0.elapsed_time(e1)
-        sampler.stop_flag = True
         it_done, stopped = eng.nes_status()
         assert not stopped and it_done == W + 2 * K, (it_done, stopped)
         rows = eng.voiced_rows()
@@ -295,6 +294,7 @@ def main():
         fb3.attack(audio, None, threshold=theta)
         t_attack = time.perf_counter() - t0
         barrier()
+        sampler.stop_flag = True
 
     def max_over_ranks(x):
         if not multi:

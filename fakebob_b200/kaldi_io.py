@@ -116,35 +116,28 @@ class _In:
             r = self.int32()
             c = self.int32()
             return np.frombuffer(self.f.read(r * c * dt.itemsize), dtype=dt).reshape(r, c).copy()
-        self.expect("[")
-        rows, cur = [], []
-        while True:
-            self._skip_line_ws(cur, rows)
-            t = self.token()
-            if t == "]":
-                if cur:
-                    rows.append(cur)
-                break
-            if t == "":
-                raise KaldiFormatError("unterminated text matrix")
-            cur.append(float(t))
+        rows = self._text_rows()
         if not rows:
             return np.zeros((0, 0), dtype=np.float64)
         return np.asarray(rows, dtype=np.float64)
 
-    def _skip_line_ws(self, cur, rows):
-        # consume whitespace; a newline terminates the current row
+    def _text_rows(self):
+        """Text matrix body: '[' then rows separated by newlines, terminated by ']'."""
+        self.expect("[")
+        buf = bytearray()
         while True:
             c = self.f.read(1)
             if not c:
-                return
-            if c == b"\n":
-                if cur:
-                    rows.append(list(cur))
-                    cur.clear()
-            elif c not in b" \t\r":
-                self.f.seek(-1, io.SEEK_CUR)
-                return
+                raise KaldiFormatError("unterminated text matrix")
+            if c == b"]":
+                break
+            buf += c
+        rows = []
+        for line in buf.decode("ascii").split("\n"):
+            vals = line.split()
+            if vals:
+                rows.append([float(v) for v in vals])
+        return rows
 
     def sp_matrix(self):
         """Packed symmetric matrix -> full (n, n)."""
@@ -164,17 +157,7 @@ class _In:
         return full
 
     def matrix_ragged(self):
-        self.expect("[")
-        rows, cur = [], []
-        while True:
-            self._skip_line_ws(cur, rows)
-            t = self.token()
-            if t == "]":
-                if cur:
-                    rows.append(cur)
-                break
-            cur.append(float(t))
-        return rows
+        return self._text_rows()
 
 
 class _Out:

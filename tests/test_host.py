@@ -1,0 +1,197 @@
+"""Host-side logic that needs no GPU: Kaldi file formats, config parsing, input conventions, the C-ABI library
+loading and exporting every declared symbol, loud failure without a GPU, and the S-sharding scheme over gloo."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from fakebob_b200 import kaldi_io, synth
+from fakebob_b200.config import FeatureConfig, load_feature_config
+from fakebob_b200.engine import to_audio_list
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_kaldi_io_round_trips(tmp_path):
+    r = np.random.default_rng(0)
+    C, D, R, L = 6, 72, 10, 5
+    w = r.dirichlet(np.ones(C)).astype(np.float32)
+    miv = r.standard_normal((C, D)).astype(np.float32)
+    iv = r.uniform(0.5, 2, (C, D)).astype(np.float32)
+    p = str(tmp_path / "a.gmm")
+    kaldi_io.write_diag_gmm(p, w, miv, iv)
+    g = kaldi_io.read_diag_gmm(p)
+    assert np.array_equal(g["weights"], w) and np.array_equal(g["means_invvars"], miv) and np.array_equal(g["inv_vars"], iv)
+    assert np.allclose(g["gconsts"], kaldi_io.diag_gconsts(w, miv, iv))
+    with open(p, "rb") as f:
+        assert f.read(12) == b"\0B<DiagGMM> "
+    ic = np.stack([np.eye(D) * (1 + i) + 0.01 for i in range(C)])
+    p = str(tmp_path / "f.ubm")
+    kaldi_io.write_full_gmm(p, w, miv, ic, np.zeros(C))
+    fg = kaldi_io.read_full_gmm(p)
+    assert fg["inv_covars"].shape == (C, D, D) and np.allclose(fg["inv_covars"], ic)
+    M = r.standard_normal((C, D, R))
+    p = str(tmp_path / "final.ie")
+    kaldi_io.write_ivector_extractor(p, w, M, ic, 100.0)
+    ie = kaldi_io.read_ivector_extractor(p)
+    assert np.array_equal(ie["M"], M) and ie["prior_offset"] == 100.0 and ie["w"].size == 0 and np.allclose(ie["sigma_inv"], ic)
+    p = str(tmp_path / "plda")
+    kaldi_io.write_plda(p, np.arange(L), np.eye(L), np.arange(L) + 1.0)
+    pl = kaldi_io.read_plda(p)
+    assert np.array_equal(pl["psi"], np.arange(L) + 1.0) and pl["transform"].shape == (L, L)
+    for binary in (True, False):
+        p = str(tmp_path / ("m%d.mat" % binary))
+        m = r.standard_normal((3, 4)).astype(np.float32)
+        kaldi_io.write_matrix(p, m, binary=binary)
+        assert np.allclose(kaldi_io.read_matrix(p), m, rtol=1e-6)
+        p = str(tmp_path / ("v%d.vec" % binary))
+        kaldi_io.write_vector(p, m[0], binary=binary)
+        assert np.allclose(kaldi_io.read_vector(p), m[0], rtol=1e-6)
+
+
+def test_text_ark_scp_targets(tmp_path):
+    v = {"a-1": np.array([1.5, -2.25, 3.0]), "b-2": np.array([0.1234567891, 7.0, -8.0])}
+    t = kaldi_io.write_text_vector_ark(str(tmp_path / "ivector.1.ark"), list(v.items()))
+    assert re.match(r".*ivector\.1\.ark:\d+$", t["b-2"])
+    assert np.allclose(kaldi_io.read_vector(t["a-1"]), v["a-1"])
+    assert np.allclose(kaldi_io.read_vector(t["b-2"]), [0.1234568, 7.0, -8.0])       # 7 significant digits ('ark,t')
+
+
+def test_feature_config_from_pre_models(tmp_path):
+    synth.write_conf(str(tmp_path))
+    cfg = load_feature_config(str(tmp_path))
+    assert (cfg.num_mel_bins, cfg.num_ceps, cfg.snip_edges, cfg.high_freq) == (30, 24, False, 7600.0)
+    assert (cfg.delta_window, cfg.delta_order, cfg.vad_energy_threshold) == (3, 2, 5.5)
+    assert cfg.num_frames(80000) == 500 and cfg.feat_dim == 72
+    cfg.check_supported()
+    bad = FeatureConfig(num_ceps=13)
+    with pytest.raises(ValueError):
+        bad.check_supported()
+    assert load_feature_config(str(tmp_path / "missing")).num_mel_bins == 30
+
+
+def test_audio_input_conventions():
+    a = np.linspace(-0.5, 0.5, 100)
+    for arr in (a, a[:, None], a[None, :]):
+        lst = to_audio_list(arr)
+        assert len(lst) == 1 and lst[0].shape == (100,) and lst[0].dtype == np.int16
+    lst = to_audio_list(np.stack([a, -a], axis=1))
+    assert len(lst) == 2 and np.array_equal(lst[1], (-a * 32768).astype(np.int16))
+    lst = to_audio_list([a[:10], np.arange(7, dtype=np.int16)])
+    assert [x.shape[0] for x in lst] == [10, 7] and np.array_equal(lst[1], np.arange(7))
+    assert to_audio_list(np.array([1.9 / 32768, -1.9 / 32768]))[0].tolist() == [1, -1]
+
+
+def test_library_exports_every_declared_symbol():
+    from fakebob_b200 import _lib
+    lib = _lib.load()
+    with open(os.path.join(ROOT, "include", "fakebob_b200.h")) as f:
+        declared = set(re.findall(r"\b(fb_[a-z0-9_]+)\s*\(", f.read()))
+    assert declared, "no declarations found"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), name
+        assert name in _lib.EXPORTS, "no ctypes prototype for " + name
+    assert lib.fb_version() >= 100
+
+
+def test_fails_loudly_without_gpu_or_device_model():
+    import torch
+    from fakebob_b200 import _lib
+    from fakebob_b200.FAKEBOB import FakeBob
+    if not torch.cuda.is_available():
+        h = ctypes.c_void_p()
+        rc = _lib.load().fb_ctx_create(0, ctypes.byref(h))
+        assert rc < 0 and b"no CPU fallback" in _lib.load().fb_last_error()
+        from fakebob_b200.engine import GmmEngine
+        with pytest.raises(_lib.FakebobLibraryError):
+            GmmEngine([{"weights": np.ones(128, np.float32) / 128, "means_invvars": np.zeros((128, 72), np.float32),
+                        "inv_vars": np.ones((128, 72), np.float32), "gconsts": np.zeros(128, np.float32)}])
+
+    class Stub:
+        def score(self, a):
+            return 0.0
+    with pytest.raises(TypeError):
+        FakeBob("SV", "untargeted", Stub())
+
+
+def test_synthetic_tree_layout(small_tree):
+    t = small_tree
+    assert os.path.exists(os.path.join(t["pre_model_dir"], "final.dubm"))
+    assert os.path.exists(os.path.join(t["pre_model_dir"], "conf", "mfcc.conf"))
+    with open(os.path.join(t["model_dir"], t["spk_ids"][0] + ".gmm"), "rb") as f:
+        m = pickle.load(f)
+    assert len(m) == 5 and m[0] == t["spk_ids"][0] and os.path.isabs(m[2]) and m[2].endswith("-identity.gmm")
+    g = kaldi_io.read_diag_gmm(m[2])
+    u = kaldi_io.read_diag_gmm(t["ubm"])
+    assert np.array_equal(g["inv_vars"], u["inv_vars"]) and not np.array_equal(g["means_invvars"], u["means_invvars"])
+
+
+# ---- multi-GPU scheme on CPU: pairs sharded over 2 gloo ranks, one all-reduce of [grad | losses | scores] -------
+def _shard_worker(rank, world, port, q):
+    import sys
+    import torch.distributed as dist
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from stub_scorer import StubScorer, make_audio
+    from fakebob_b200.sharding import pair_range, global_column
+    from oracle.nes import margin_loss
+    from oracle import philox
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, S, K, sigma, seed, it = 4000, 10, 3, 1e-3, 5, 2
+    model = StubScorer(K, N)
+    audio = make_audio(1)[:, None]
+    p0, p1 = pair_range(S // 2, rank, world)
+    noise = philox.normal_noise(seed, it, N, S // 2)[:, p0:p1]
+    cols = [0] if rank == 0 else []
+    batch = [audio] if rank == 0 else []
+    batch += [sigma * noise + audio, sigma * (-1.0 * noise) + audio]
+    cols += [global_column(S // 2, p0 + j, +1) for j in range(p1 - p0)] + [global_column(S // 2, p0 + j, -1) for j in range(p1 - p0)]
+    scores = model.score(np.concatenate(batch, axis=1))
+    loss = margin_loss(scores, "OSI", "untargeted", 2.5, 0.0).reshape(-1)
+    red = np.zeros(N + S + 1 + K)
+    red[N + np.array(cols)] = loss
+    if rank == 0:
+        red[N + S + 1:] = scores[0]
+        loc = loss[1:]
+    else:
+        loc = loss
+    npairs = p1 - p0
+    red[:N] = (loc[:npairs] * noise).sum(axis=1) + (loc[npairs:] * (-1.0 * noise)).sum(axis=1)
+    t = torch.from_numpy(red)
+    dist.all_reduce(t)
+    if rank == 0:
+        q.put(t.numpy().copy())
+    dist.destroy_process_group()
+
+
+def test_sharded_gradient_allreduce_matches_single_process_gloo():
+    import sys
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from stub_scorer import StubScorer, make_audio
+    from oracle.nes import OracleFakeBob, PhiloxNoise
+    from fakebob_b200.sharding import pair_range
+    assert [pair_range(25, r, 8) for r in range(8)] == [(0, 3), (3, 6), (6, 9), (9, 12), (12, 15), (15, 18), (18, 21), (21, 25)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    red = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    N, S, K = 4000, 10, 3
+    fb = OracleFakeBob("OSI", "untargeted", StubScorer(K, N), samples_per_draw=S, sigma=1e-3, noise_fn=PhiloxNoise(5))
+    fb.threshold = 2.5
+    fb.draws = 2
+    final_loss, grad, adver_loss, score = fb.get_grad(make_audio(1))
+    assert np.allclose(red[:N] / S / 1e-3, grad[:, 0], rtol=1e-12, atol=1e-12)
+    assert red[N] == adver_loss[0] and np.isclose(red[N + 1:N + 1 + S].mean(), final_loss, rtol=1e-14)
+    assert np.array_equal(red[N + S + 1:], score)
