@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfakebob_b200.so")
-SOURCES = ["fb_api.cu", "fb_frontend.cu", "fb_gmm.cu", "fb_nes.cu", "fb_comm.cu"]
-HEADERS = ["fb_common.cuh", "fb_nes.cuh", os.path.join("..", "..", "include", "fakebob_b200.h")]
+SOURCES = ["fb_api.cu", "fb_frontend.cu", "fb_gmm.cu", "fb_nes.cu", "fb_comm.cu", "fb_ivector.cu"]
+HEADERS = ["fb_common.cuh", "fb_nes.cuh", "fb_ivector.cuh", os.path.join("..", "..", "include", "fakebob_b200.h")]
 
 
 def _newest(paths):

@@ -2,6 +2,7 @@
 // See include/fakebob_b200.h for the reference call each entry point replaces.
 #include "fb_common.cuh"
 #include "fb_nes.cuh"
+#include "fb_ivector.cuh"
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
@@ -72,6 +73,7 @@ extern "C" int fb_ctx_destroy(fb_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   fb_nes_destroy(ctx);
+  fb_ivector_destroy(ctx);
   fb_comm_destroy_impl(ctx);
   ctx->w_img.release(); ctx->gconst2.release(); ctx->w_f32.release(); ctx->gconst_nat.release();
   ctx->wave.release(); ctx->wave_off.release(); ctx->frame_off.release(); ctx->mfcc.release();
@@ -131,7 +133,7 @@ static int check_voiced(fb_ctx *ctx) {
   if (misc[1] != 0) {
     const int zero = 0;
     cudaMemcpy(ctx->misc.p + 1, &zero, sizeof(int), cudaMemcpyHostToDevice);
-    fb_set_error("utterance %d has no voiced frames (Kaldi's select-voiced-frames would drop it)", misc[1] - 1);
+    fb_set_error("utterance %d has no voiced frames (Kaldi's select-voiced-frames would drop it)", misc[1] - 16);
     return FB_ERR_NO_VOICED;
   }
   return FB_OK;
@@ -214,7 +216,7 @@ static int total_rows(fb_ctx *ctx, int *rows) {
 
 extern "C" int fb_get_features(fb_ctx *ctx, float *out_host, int64_t capacity_floats) {
   FB_CHECK_ARG(ctx && out_host, "NULL argument");
-  FB_CHECK_ARG(ctx->debug_feats, "fb_set_debug(ctx, 1) must be called before scoring");
+  FB_CHECK_ARG(ctx->debug_feats || ctx->need_feats_f32, "fb_set_debug(ctx, 1) must be called before scoring");
   int rows = 0, rc;
   if ((rc = total_rows(ctx, &rows))) return rc;
   FB_CHECK_ARG(capacity_floats >= (int64_t)rows * FB_DIM, "output buffer too small");

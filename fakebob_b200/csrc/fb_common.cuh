@@ -91,6 +91,7 @@ struct FbHostGmm {
 };
 
 struct FbNes;   // fb_nes.cu
+struct FbIvector;  // fb_ivector.cu
 struct FbComm;  // fb_comm.cu
 
 struct fb_ctx {
@@ -144,6 +145,9 @@ struct fb_ctx {
   double prof_ms[FB_PROF_STAGES] = {0};
   int64_t prof_cnt[FB_PROF_STAGES] = {0};
 
+  int arch = 0;                // 0 = GMM-UBM scoring, 1 = i-vector / PLDA scoring
+  bool need_feats_f32 = false; // the i-vector path consumes the float32 features
+  FbIvector *iv = nullptr;
   FbNes *nes = nullptr;
   FbComm *comm = nullptr;
   int64_t launches = 0;

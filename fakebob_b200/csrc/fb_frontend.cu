@@ -302,7 +302,7 @@ vad_scan_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_of
   }
   if (tid == 0) {
     nvoiced[b] = running;
-    if (running == 0) atomicExch(&misc[1], 1 + b);
+    if (running == 0) atomicExch(&misc[1], 16 + b);
     __threadfence();
     int ticket = atomicAdd(&misc[0], 1);
     s_flag = (ticket == (int)gridDim.x - 1);
@@ -529,7 +529,7 @@ int fb_reserve_batch(fb_ctx *ctx, int B, const int64_t *offsets_host) {
     if ((rc = ctx->frame_ll.ensure((size_t)ctx->n_models * ctx->rows_cap))) return rc;
     if ((rc = ctx->avg_ll.ensure((size_t)B * ctx->n_models))) return rc;
   }
-  if (ctx->debug_feats)
+  if (ctx->debug_feats || ctx->need_feats_f32)
     if ((rc = ctx->feats_f32.ensure((size_t)total_frames * FB_DIM))) return rc;
   if (fb_feats_smem_bytes(max_frames) > FB_FEATS_SMEM_MAX) {
     if ((rc = ctx->raw72.ensure((size_t)total_frames * FB_DIM))) return rc;
@@ -560,7 +560,7 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   }
   feats_kernel<<<dim3(9, B), FEATS_THREADS, use_smem ? smem : 0, ctx->stream>>>(
       ctx->mfcc.p, ctx->frame_off.p, ctx->vrank.p, ctx->row_off.p, ctx->tables_dev, ctx->a_img.p,
-      ctx->debug_feats ? ctx->feats_f32.p : nullptr, use_smem ? nullptr : ctx->raw72.p,
+      (ctx->debug_feats || ctx->need_feats_f32) ? ctx->feats_f32.p : nullptr, use_smem ? nullptr : ctx->raw72.p,
       use_smem ? nullptr : ctx->cmn_prefix.p, use_smem, done_flag);
   fb_prof_mark(ctx, 3);
   ctx->launches += 3;

@@ -163,6 +163,7 @@ struct GmmArgs {
   float2 *part;             // [model][C/128][rows_cap]
   const int *misc;          // misc[2] = total voiced rows
   const int *done_flag;
+  float *ll_out;            // STORE mode: [rows_cap][C] natural-log component log-likelihoods (Gaussian selection)
   int n_models, C, rows_cap;
 };
 
@@ -192,6 +193,7 @@ __device__ __forceinline__ void lse_group(const float *v, float &m, float &s) {
   s += s0 + s1;
 }
 
+template <bool kStore>
 __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   if (g.done_flag && *g.done_flag) return;
   extern __shared__ uint8_t smem_raw[];
@@ -356,11 +358,23 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * tile);     // accumulator is in registers: MMA may overwrite
         ++sub;
-        lse_group(va, m, s);
-        lse_group(vb, m, s);
+        if (kStore) {
+          const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
+          float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + ch * FB_CHUNK_N + h * FB_STAGE_N);
+          const float ln2 = 0.6931471805599453f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(va[i] * ln2, va[i + 1] * ln2, va[i + 2] * ln2, va[i + 3] * ln2);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) dst[8 + (i >> 2)] = make_float4(vb[i] * ln2, vb[i + 1] * ln2, vb[i + 2] * ln2, vb[i + 3] * ln2);
+        } else {
+          lse_group(va, m, s);
+          lse_group(vb, m, s);
+        }
       }
-      const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
-      g.part[((size_t)model * nch + ch) * g.rows_cap + row] = make_float2(m, s);
+      if (!kStore) {
+        const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
+        g.part[((size_t)model * nch + ch) * g.rows_cap + row] = make_float2(m, s);
+      }
     }
   }
   tc_fence_before();
@@ -564,7 +578,8 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
   ctx->avg_ll.release();
   static bool attr_set = false;
   if (!attr_set) {
-    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
     attr_set = true;
   }
   return FB_OK;
@@ -587,7 +602,8 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * ctx->n_models * nch;
     int grid = ctx->num_sms;
     if (max_units < grid) grid = (int)max_units;
-    gmm_umma_kernel<<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
+    a.ll_out = nullptr;
+    gmm_umma_kernel<false><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
   } else {
     dim3 grid(fb_div_up(ctx->total_frames, 32), ctx->n_models * nch);
     gmm_simt_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->a_img.p, ctx->w_f32.p, ctx->gconst_nat.p,
@@ -605,3 +621,27 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
 }
 
 int fb_run_gmm(fb_ctx *ctx) { return fb_run_gmm_flag(ctx, nullptr); }
+
+// Gaussian-selection pass of the i-vector path: slot 0 only, raw component log-likelihoods to ll_out [rows_cap][C].
+int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag) {
+  FB_CHECK_ARG(ctx->n_models >= 1, "no GMMs loaded");
+  const int nch = ctx->C / FB_CHUNK_N;
+  GmmArgs a;
+  a.a_img = ctx->a_img.p;
+  a.w_img = ctx->w_img.p;
+  a.part = nullptr;
+  a.misc = ctx->misc.p;
+  a.done_flag = done_flag;
+  a.ll_out = ll_out;
+  a.n_models = 1;
+  a.C = ctx->C;
+  a.rows_cap = ctx->rows_cap;
+  const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * nch;
+  int grid = ctx->num_sms;
+  if (max_units < grid) grid = (int)max_units;
+  gmm_umma_kernel<true><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
+  fb_prof_mark(ctx, 4);
+  ctx->launches += 1;
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}

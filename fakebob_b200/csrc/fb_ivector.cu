@@ -1,0 +1,808 @@
+// i-vector extraction + PLDA scoring on the device.
+//
+// Replaces sid/extract_ivectors.sh and ivector-plda-scoring as the reference runs them per score() call
+// (ivector_PLDA_kaldiHelper.py:202-211, 262-271); upstream arithmetic SURVEY.md Appendix A.8:
+//   gselect_kernel     gmm-gselect --n=20 on the diagonalised full UBM (log-likelihoods from the tcgen05 GMM kernel in
+//                      STORE mode), best-first indices
+//   fgmm_post_kernel   fgmm-global-gselect-to-post --min-post=0.025: 20 full-covariance log-likelihoods per frame (float),
+//                      softmax, pruning, renormalisation
+//   ivec_stats_kernel  Baum-Welch statistics gamma_c, X_c per utterance (float64, frame order like Kaldi's AccStats)
+//   ivec_lin_kernel    lin  = sum_c (Sigma_c^-1 M_c)^T X_c              (fp32 parameters streamed once, float64 accumulation)
+//   ivec_quad_kernel   quad = sum_c gamma_c vech(M_c^T Sigma_c^-1 M_c)  (idem)
+//   ivec_solve_kernel  (quad + I) w = lin + prior e_0   by Cholesky (float64), w_0 -= prior offset, stored as float
+//   plda_kernel        ivector-subtract-global-mean | transform-vec | ivector-normalize-length (float), Plda::TransformIvector
+//                      (normalize_length, float64), LogLikelihoodRatio against every enrolled speaker
+// The derived extractor matrices (Sigma^-1 M, U) are computed ONCE at load on the device (Kaldi recomputes them on every
+// ivector-extract invocation).
+#include "fb_common.cuh"
+#include "fb_ivector.cuh"
+#include <math.h>
+#include <string.h>
+
+int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag);
+int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag);
+
+#define IV_NSEL 20
+
+// ------------------------------------------------------------------------------------------------
+// Top-20 Gaussian selection: one warp per frame; lanes hold C/32 values each (C <= 2048).
+// Ties resolve to the lower component index (stable descending sort).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C, int *__restrict__ gsel,
+               const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= misc[2]) return;
+  const int per = C >> 5;
+  float v[64];
+  const float *src = ll + (size_t)row * C;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = (i < per) ? src[lane + 32 * i] : -INFINITY;
+  float best = -INFINITY;
+  int bi = 0;
+#pragma unroll
+  for (int i = 0; i < 64; ++i)
+    if (v[i] > best) { best = v[i]; bi = i; }
+  for (int k = 0; k < IV_NSEL; ++k) {
+    float wv = best;
+    int wi = lane + 32 * bi;                      // component index
+    int wl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+      if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; wl = ol; }
+    }
+    if (lane == 0) gsel[(size_t)row * IV_NSEL + k] = wi;
+    if (lane == wl) {
+      const int slot = wi >> 5;
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        if (i == slot) v[i] = -INFINITY;
+      best = -INFINITY;
+      bi = 0;
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        if (v[i] > best) { best = v[i]; bi = i; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full-covariance log-likelihoods of the 20 selected components + posteriors.  One warp per frame.
+// inv_covars are packed lower-triangular row-major (Kaldi SpMatrix), D = 72 -> 2628 entries.
+// ------------------------------------------------------------------------------------------------
+#define IV_PACKED (FB_DIM * (FB_DIM + 1) / 2)
+
+__global__ void __launch_bounds__(256)
+fgmm_post_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, const float *__restrict__ gconsts,
+                 const float *__restrict__ means_invcovars, const float *__restrict__ inv_covars_packed,
+                 const unsigned short *__restrict__ rc_table, const int *__restrict__ misc, float min_post,
+                 float *__restrict__ post, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  __shared__ float s_x[8][FB_DIM];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + w;
+  if (row >= misc[2]) return;
+  for (int d = lane; d < FB_DIM; d += 32) s_x[w][d] = feats[(size_t)row * FB_DIM + d];
+  __syncwarp();
+  float my_ll = -INFINITY;
+  for (int j = 0; j < IV_NSEL; ++j) {
+    const int c = gsel[(size_t)row * IV_NSEL + j];
+    const float *S = inv_covars_packed + (size_t)c * IV_PACKED;
+    float q = 0.f;
+    for (int e = lane; e < IV_PACKED; e += 32) {
+      const unsigned short rc = rc_table[e];
+      const int r = rc >> 8, cc = rc & 255;
+      const float xx = s_x[w][r] * s_x[w][cc];
+      q += S[e] * ((r == cc) ? 0.5f * xx : xx);
+    }
+    float lin = 0.f;
+    for (int d = lane; d < FB_DIM; d += 32) lin += means_invcovars[(size_t)c * FB_DIM + d] * s_x[w][d];
+    float tot = lin - q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == j) my_ll = gconsts[c] + tot;
+  }
+  // softmax over lanes 0..19 (VectorBase::ApplySoftMax: float exp, sequential float sum, Scale(1/sum))
+  float m = my_ll;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float e = (lane < IV_NSEL) ? expf(my_ll - m) : 0.f;
+  float sum = 0.f;
+  for (int j = 0; j < IV_NSEL; ++j) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, e, j));
+  float p = e * (float)(1.0 / (double)sum);
+  if (min_post != 0.f) {
+    // argmax (first maximum), prune, renormalise (fgmm-global-gselect-to-post.cc)
+    float bv = (lane < IV_NSEL) ? p : -1.f;
+    int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+    }
+    if (p < min_post) p = 0.f;
+    double s2 = 0.0;
+    for (int j = 0; j < IV_NSEL; ++j) s2 += (double)__shfl_sync(0xffffffffu, p, j);
+    const float s2f = (float)s2;
+    if (s2f == 0.f) p = (lane == bl) ? 1.f : 0.f;
+    else p = p * (float)(1.0 / (double)s2f);
+  }
+  if (lane < IV_NSEL) post[(size_t)row * IV_NSEL + lane] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Baum-Welch statistics per utterance: gamma[b][c], X[b][c][72] (float64, dense).  One CTA per utterance.
+// Pairs are bucketed by component in shared memory, each bucket is put in frame order (rank sort), then one warp
+// per component accumulates sequentially -- the same order as Kaldi's per-frame AccStats, deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, const float *__restrict__ post,
+                  const int *__restrict__ row_off, int C, int max_pairs, double *__restrict__ gamma,
+                  double *__restrict__ Xs, int *__restrict__ err, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  extern __shared__ unsigned char s_raw[];
+  int *cnt = reinterpret_cast<int *>(s_raw);                  // [C]
+  int *off = cnt + C;                                         // [C + 1]
+  int *cur = off + C + 1;                                     // [C]
+  unsigned short *lt = reinterpret_cast<unsigned short *>(cur + C);   // [max_pairs] frame index, unsorted
+  unsigned short *ls = lt + max_pairs;                        // [max_pairs] sorted
+  float *lp = reinterpret_cast<float *>(ls + max_pairs + (max_pairs & 1));   // [max_pairs] unsorted
+  float *lq = lp + max_pairs;                                 // [max_pairs] sorted
+  __shared__ int s_scan[256];
+  const int b = blockIdx.x;
+  const int r0 = row_off[b], Tv = row_off[b + 1] - r0;
+  const int tid = threadIdx.x;
+  if (Tv * IV_NSEL > max_pairs) {
+    if (tid == 0) atomicExch(err, 2);
+    return;
+  }
+  for (int c = tid; c < C; c += blockDim.x) { cnt[c] = 0; cur[c] = 0; }
+  __syncthreads();
+  for (int i = tid; i < Tv * IV_NSEL; i += blockDim.x)
+    if (post[(size_t)r0 * IV_NSEL + i] != 0.f) atomicAdd(&cnt[gsel[(size_t)r0 * IV_NSEL + i]], 1);
+  __syncthreads();
+  // exclusive scan of cnt (C <= 2048: 8 per thread)
+  const int per = (C + 255) / 256;
+  int local = 0;
+  for (int k = 0; k < per; ++k) { const int c = tid * per + k; if (c < C) local += cnt[c]; }
+  s_scan[tid] = local;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; ++i) { const int t = s_scan[i]; s_scan[i] = run; run += t; }
+  }
+  __syncthreads();
+  int run = s_scan[tid];
+  for (int k = 0; k < per; ++k) { const int c = tid * per + k; if (c < C) { off[c] = run; run += cnt[c]; } }
+  if (tid == 255) off[C] = run;
+  __syncthreads();
+  for (int i = tid; i < Tv * IV_NSEL; i += blockDim.x) {
+    const float p = post[(size_t)r0 * IV_NSEL + i];
+    if (p != 0.f) {
+      const int c = gsel[(size_t)r0 * IV_NSEL + i];
+      const int pos = off[c] + atomicAdd(&cur[c], 1);
+      lt[pos] = (unsigned short)(i / IV_NSEL);
+      lp[pos] = p;
+    }
+  }
+  __syncthreads();
+  const int w = tid >> 5, lane = tid & 31;
+  for (int c = w; c < C; c += 8) {
+    const int n = cnt[c], o = off[c];
+    // rank sort by frame index (frame indices within a bucket are distinct)
+    for (int i = lane; i < n; i += 32) {
+      const unsigned short t = lt[o + i];
+      int rank = 0;
+      for (int k = 0; k < n; ++k) rank += (lt[o + k] < t) ? 1 : 0;
+      ls[o + rank] = t;
+      lq[o + rank] = lp[o + i];
+    }
+    __syncwarp();
+    double g = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double p = (double)lq[o + i];
+      const float *xr = feats + (size_t)(r0 + ls[o + i]) * FB_DIM;
+      g += p;
+      x0 += p * (double)xr[lane];
+      x1 += p * (double)xr[lane + 32];
+      if (lane < 8) x2 += p * (double)xr[lane + 64];
+    }
+    double *xo = Xs + ((size_t)b * C + c) * FB_DIM;
+    xo[lane] = x0;
+    xo[lane + 32] = x1;
+    if (lane < 8) xo[lane + 64] = x2;
+    if (lane == 0) gamma[(size_t)b * C + c] = g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Derived extractor parameters (once, at load): SIM[c] = Sigma_inv[c] * M[c] (D x R),  U[c] = vech(M[c]^T SIM[c]).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ivec_derive_sim_kernel(const double *__restrict__ M, const double *__restrict__ sigma_inv, int R, double *__restrict__ sim64,
+                       float *__restrict__ sim32) {
+  const int c = blockIdx.x;
+  for (int idx = threadIdx.x; idx < FB_DIM * R; idx += blockDim.x) {
+    const int d = idx / R, r = idx - d * R;
+    double acc = 0.0;
+    for (int e = 0; e < FB_DIM; ++e) acc += sigma_inv[((size_t)c * FB_DIM + d) * FB_DIM + e] * M[((size_t)c * FB_DIM + e) * R + r];
+    sim64[(size_t)c * FB_DIM * R + idx] = acc;
+    sim32[(size_t)c * FB_DIM * R + idx] = (float)acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ivec_derive_u_kernel(const double *__restrict__ M, const double *__restrict__ sim64, int R, int n_packed, float *__restrict__ U) {
+  const int c = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_packed) return;
+  // packed lower-triangular index e -> (r, s), s <= r
+  int r = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+  while ((r + 1) * (r + 2) / 2 <= e) ++r;
+  while (r * (r + 1) / 2 > e) --r;
+  const int s = e - r * (r + 1) / 2;
+  double acc = 0.0;
+  for (int d = 0; d < FB_DIM; ++d) acc += M[((size_t)c * FB_DIM + d) * R + r] * sim64[((size_t)c * FB_DIM + d) * R + s];
+  U[(size_t)c * n_packed + e] = (float)acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lin partials: each CTA owns a contiguous range of components and all R columns; thread r accumulates IV_BCHUNK
+// utterances in float64 registers.  grid (n_splits, ceil(B / IV_BCHUNK)), block = R rounded up to 32.
+// ------------------------------------------------------------------------------------------------
+#define IV_BCHUNK 32
+
+__global__ void __launch_bounds__(512)
+ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, const double *__restrict__ gamma, int B, int C,
+                int R, int n_splits, double *__restrict__ part, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  __shared__ double s_x[IV_BCHUNK][FB_DIM];
+  __shared__ int s_act[IV_BCHUNK];
+  const int split = blockIdx.x;
+  const int b0 = blockIdx.y * IV_BCHUNK;
+  const int nb = min(IV_BCHUNK, B - b0);
+  const int c0 = (int)((long long)C * split / n_splits), c1 = (int)((long long)C * (split + 1) / n_splits);
+  const int r = threadIdx.x;
+  double acc[IV_BCHUNK];
+#pragma unroll
+  for (int i = 0; i < IV_BCHUNK; ++i) acc[i] = 0.0;
+  for (int c = c0; c < c1; ++c) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nb * FB_DIM; idx += blockDim.x) {
+      const int i = idx / FB_DIM, d = idx - i * FB_DIM;
+      s_x[i][d] = Xs[((size_t)(b0 + i) * C + c) * FB_DIM + d];
+    }
+    if (threadIdx.x < nb) s_act[threadIdx.x] = gamma[(size_t)(b0 + threadIdx.x) * C + c] != 0.0;
+    __syncthreads();
+    if (r < R) {
+      const float *col = sim32 + (size_t)c * FB_DIM * R + r;
+      for (int d = 0; d < FB_DIM; ++d) {
+        const double sv = (double)col[(size_t)d * R];
+#pragma unroll
+        for (int i = 0; i < IV_BCHUNK; ++i)
+          if (i < nb && s_act[i]) acc[i] += sv * s_x[i][d];
+      }
+    }
+  }
+  if (r < R)
+#pragma unroll
+    for (int i = 0; i < IV_BCHUNK; ++i)
+      if (i < nb) part[((size_t)split * B + b0 + i) * R + r] = acc[i];
+}
+
+// quad: thread = packed entry e; accumulates IV_BCHUNK utterances; gamma staged through shared memory in chunks.
+// grid (ceil(n_packed / 256), ceil(B / IV_BCHUNK)).
+__global__ void __launch_bounds__(256)
+ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, int B, int C, int n_packed,
+                 double *__restrict__ quad, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  __shared__ double s_g[IV_BCHUNK][128];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * IV_BCHUNK;
+  const int nb = min(IV_BCHUNK, B - b0);
+  double acc[IV_BCHUNK];
+#pragma unroll
+  for (int i = 0; i < IV_BCHUNK; ++i) acc[i] = 0.0;
+  for (int cb = 0; cb < C; cb += 128) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nb * 128; idx += blockDim.x) {
+      const int i = idx >> 7, k = idx & 127;
+      s_g[i][k] = (cb + k < C) ? gamma[(size_t)(b0 + i) * C + cb + k] : 0.0;
+    }
+    __syncthreads();
+    if (e < n_packed) {
+      const int kmax = min(128, C - cb);
+      for (int k = 0; k < kmax; ++k) {
+        const double u = (double)U[(size_t)(cb + k) * n_packed + e];
+#pragma unroll
+        for (int i = 0; i < IV_BCHUNK; ++i) {
+          const double gk = s_g[i][k];
+          if (i < nb && gk != 0.0) acc[i] += gk * u;
+        }
+      }
+    }
+  }
+  if (e < n_packed)
+#pragma unroll
+    for (int i = 0; i < IV_BCHUNK; ++i)
+      if (i < nb) quad[(size_t)(b0 + i) * n_packed + e] = acc[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per utterance: A = unpack(quad) + I, rhs = sum of lin partials (+ prior offset on element 0), Cholesky solve.
+// One CTA (512 threads) per utterance; A lives in global scratch [b][R][R] (L2 resident).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ lin_part, int n_splits, int B, int R, int n_packed,
+                  double prior_offset, double *__restrict__ Awork, float *__restrict__ ivec, int *__restrict__ err,
+                  const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  extern __shared__ double s_v[];            // [R] rhs / solution, [R] column scratch
+  double *rhs = s_v, *colk = s_v + R;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  double *A = Awork + (size_t)b * R * R;
+  for (int idx = tid; idx < R * R; idx += nt) {
+    const int i = idx / R, j = idx - i * R;
+    if (j <= i) A[idx] = quad[(size_t)b * n_packed + (size_t)i * (i + 1) / 2 + j] + ((i == j) ? 1.0 : 0.0);
+  }
+  for (int r = tid; r < R; r += nt) {
+    double acc = 0.0;
+    for (int s = 0; s < n_splits; ++s) acc += lin_part[((size_t)s * B + b) * R + r];
+    rhs[r] = acc + ((r == 0) ? prior_offset : 0.0);
+  }
+  __syncthreads();
+  // right-looking Cholesky on the lower triangle
+  for (int k = 0; k < R; ++k) {
+    const double akk = A[(size_t)k * R + k];
+    if (!(akk > 0.0)) { if (tid == 0) atomicExch(err, 3); return; }
+    const double d = sqrt(akk);
+    __syncthreads();
+    for (int i = k + tid; i < R; i += nt) {
+      const double v = (i == k) ? d : A[(size_t)i * R + k] / d;
+      A[(size_t)i * R + k] = v;
+      colk[i] = v;
+    }
+    __syncthreads();
+    const int rem = R - k - 1;
+    // trailing update: rows i > k, columns k < j <= i ; warps take rows, lanes take columns (coalesced)
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int ii = warp; ii < rem; ii += nw) {
+      const int i = k + 1 + ii;
+      const double lik = colk[i];
+      for (int j = k + 1 + lane; j <= i; j += 32) A[(size_t)i * R + j] -= lik * colk[j];
+    }
+    __syncthreads();
+  }
+  // forward substitution L y = rhs (column oriented), then backward L^T w = y
+  for (int k = 0; k < R; ++k) {
+    if (tid == 0) rhs[k] = rhs[k] / A[(size_t)k * R + k];
+    __syncthreads();
+    const double yk = rhs[k];
+    for (int i = k + 1 + tid; i < R; i += nt) rhs[i] -= A[(size_t)i * R + k] * yk;
+    __syncthreads();
+  }
+  for (int k = R - 1; k >= 0; --k) {
+    if (tid == 0) rhs[k] = rhs[k] / A[(size_t)k * R + k];
+    __syncthreads();
+    const double wk = rhs[k];
+    for (int i = tid; i < k; i += nt) rhs[i] -= A[(size_t)k * R + i] * wk;
+    __syncthreads();
+  }
+  for (int r = tid; r < R; r += nt) ivec[(size_t)b * R + r] = (float)(rhs[r] - ((r == 0) ? prior_offset : 0.0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// PLDA back-end, one CTA per utterance.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+plda_kernel(const float *__restrict__ ivec, const float *__restrict__ mean_vec, const float *__restrict__ lda, int lda_cols,
+            const double *__restrict__ plda_T, const double *__restrict__ plda_off, const double *__restrict__ psi,
+            const double *__restrict__ u_train, int R, int L, int K, double *__restrict__ scores,
+            const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  extern __shared__ double s_d[];
+  double *u = s_d;                                   // [L]
+  float *v = reinterpret_cast<float *>(s_d + L);    // [R] centred i-vector
+  float *t = v + R;                                  // [L] LDA output
+  __shared__ double s_red[8];
+  __shared__ double s_bcast;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int r = tid; r < R; r += blockDim.x) v[r] = __fadd_rn(ivec[(size_t)b * R + r], -mean_vec[r]);
+  __syncthreads();
+  for (int l = tid; l < L; l += blockDim.x) {
+    float acc = (lda_cols == R + 1) ? lda[(size_t)l * lda_cols + R] : 0.f;
+    for (int r = 0; r < R; ++r) acc += lda[(size_t)l * lda_cols + r] * v[r];
+    t[l] = acc;
+  }
+  __syncthreads();
+  // ivector-normalize-length: scale to norm sqrt(L)
+  double part = 0.0;
+  for (int l = tid; l < L; l += blockDim.x) part += (double)t[l] * (double)t[l];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += s_red[i];
+    const float norm = (float)sqrt(tot);
+    const float ratio = norm / sqrtf((float)L);
+    s_bcast = (double)(1.0f / ratio);
+  }
+  __syncthreads();
+  const float inv_ratio = (float)s_bcast;
+  for (int l = tid; l < L; l += blockDim.x) t[l] = t[l] * inv_ratio;
+  __syncthreads();
+  // Plda::TransformIvector (double)
+  for (int l = tid; l < L; l += blockDim.x) {
+    double acc = plda_off[l];
+    for (int k = 0; k < L; ++k) acc += plda_T[(size_t)l * L + k] * (double)t[k];
+    u[l] = acc;
+  }
+  __syncthreads();
+  part = 0.0;
+  for (int l = tid; l < L; l += blockDim.x) part += u[l] * u[l] / (psi[l] + 1.0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  __syncthreads();
+  if ((tid & 31) == 0) s_red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += s_red[i];
+    s_bcast = sqrt((double)L / tot);
+  }
+  __syncthreads();
+  const double factor = s_bcast;
+  for (int l = tid; l < L; l += blockDim.x) u[l] *= factor;
+  __syncthreads();
+  // LogLikelihoodRatio against each enrolled speaker (n = 1); one warp per speaker
+  const int w = tid >> 5, lane = tid & 31;
+  for (int k = w; k < K; k += 8) {
+    double given = 0.0, without = 0.0;
+    for (int l = lane; l < L; l += 32) {
+      const double ps = psi[l];
+      const double mean = ps / (ps + 1.0) * u_train[(size_t)k * L + l];
+      const double var = 1.0 + ps / (ps + 1.0);
+      const double d = u[l] - mean;
+      given += log(var) + d * d / var;
+      const double var0 = 1.0 + ps;
+      without += log(var0) + u[l] * u[l] / var0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      given += __shfl_xor_sync(0xffffffffu, given, o);
+      without += __shfl_xor_sync(0xffffffffu, without, o);
+    }
+    if (lane == 0) scores[(size_t)b * K + k] = -0.5 * given + 0.5 * without;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static void iv_release(FbIvector *v) {
+  if (!v) return;
+  v->gconsts.release(); v->means_invcovars.release(); v->inv_covars.release(); v->rc_table.release();
+  v->sim32.release(); v->U.release(); v->mean_vec.release(); v->lda.release(); v->plda_T.release();
+  v->plda_off.release(); v->psi.release(); v->u_train.release();
+  v->ll.release(); v->gsel.release(); v->post.release(); v->gamma.release(); v->Xs.release(); v->lin_part.release();
+  v->quad.release(); v->Awork.release(); v->ivec.release(); v->scores.release();
+  delete v;
+}
+
+void fb_ivector_destroy(fb_ctx *ctx) {
+  iv_release(ctx->iv);
+  ctx->iv = nullptr;
+}
+
+static FbIvector *iv_get(fb_ctx *ctx) {
+  if (!ctx->iv) ctx->iv = new FbIvector();
+  return ctx->iv;
+}
+
+extern "C" int fb_load_full_gmm(fb_ctx *ctx, const float *weights, const float *means_invcovars, const float *inv_covars,
+                                const float *gconsts, int C, int D) {
+  FB_CHECK_ARG(ctx && weights && means_invcovars && inv_covars && gconsts, "NULL argument");
+  FB_CHECK_ARG(D == FB_DIM, "feature dimension must be 72");
+  FB_CHECK_ARG(C > 0 && C % FB_CHUNK_N == 0 && C <= 2048, "number of components must be a multiple of 128, at most 2048");
+  FB_CUDA(cudaSetDevice(ctx->device));
+  FbIvector *v = iv_get(ctx);
+  v->C = C;
+  // packed lower-triangular copies + (row, col) table
+  std::vector<float> packed((size_t)C * IV_PACKED);
+  for (int c = 0; c < C; ++c) {
+    size_t e = 0;
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j <= i; ++j) packed[(size_t)c * IV_PACKED + e++] = inv_covars[((size_t)c * D + i) * D + j];
+  }
+  std::vector<unsigned short> rc(IV_PACKED);
+  {
+    size_t e = 0;
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j <= i; ++j) rc[e++] = (unsigned short)((i << 8) | j);
+  }
+  int rcode;
+  if ((rcode = v->gconsts.ensure(C))) return rcode;
+  if ((rcode = v->means_invcovars.ensure((size_t)C * D))) return rcode;
+  if ((rcode = v->inv_covars.ensure(packed.size()))) return rcode;
+  if ((rcode = v->rc_table.ensure(IV_PACKED))) return rcode;
+  FB_CUDA(cudaMemcpy(v->gconsts.p, gconsts, C * sizeof(float), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(v->means_invcovars.p, means_invcovars, (size_t)C * D * sizeof(float), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(v->inv_covars.p, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(v->rc_table.p, rc.data(), IV_PACKED * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  // fgmm-global-to-gmm (DiagGmm::CopyFromFullGmm): invert each covariance in double (Cholesky-free Gauss-Jordan on SPD)
+  std::vector<float> dw(weights, weights + C), dmiv((size_t)C * D), div_((size_t)C * D), dgc(C);
+  std::vector<double> a((size_t)D * D), inv((size_t)D * D);
+  for (int c = 0; c < C; ++c) {
+    for (int i = 0; i < D * D; ++i) a[i] = inv_covars[(size_t)c * D * D + i];
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) inv[(size_t)i * D + j] = (i == j) ? 1.0 : 0.0;
+    for (int k = 0; k < D; ++k) {
+      int piv = k;
+      for (int i = k + 1; i < D; ++i)
+        if (fabs(a[(size_t)i * D + k]) > fabs(a[(size_t)piv * D + k])) piv = i;
+      if (fabs(a[(size_t)piv * D + k]) < 1e-300) { fb_set_error("component %d: singular inverse covariance", c); return FB_ERR_ARG; }
+      if (piv != k)
+        for (int j = 0; j < D; ++j) { std::swap(a[(size_t)k * D + j], a[(size_t)piv * D + j]); std::swap(inv[(size_t)k * D + j], inv[(size_t)piv * D + j]); }
+      const double d = 1.0 / a[(size_t)k * D + k];
+      for (int j = 0; j < D; ++j) { a[(size_t)k * D + j] *= d; inv[(size_t)k * D + j] *= d; }
+      for (int i = 0; i < D; ++i)
+        if (i != k) {
+          const double f = a[(size_t)i * D + k];
+          if (f != 0.0)
+            for (int j = 0; j < D; ++j) { a[(size_t)i * D + j] -= f * a[(size_t)k * D + j]; inv[(size_t)i * D + j] -= f * inv[(size_t)k * D + j]; }
+        }
+    }
+    double gc = log((double)weights[c]) - 0.5 * D * 1.8378770664093454835606594728112;
+    for (int i = 0; i < D; ++i) {
+      double mean = 0.0;
+      for (int j = 0; j < D; ++j) mean += inv[(size_t)i * D + j] * (double)means_invcovars[(size_t)c * D + j];
+      const float var_f = (float)inv[(size_t)i * D + i];
+      const float iv_f = 1.0f / var_f;
+      const float mean_f = (float)mean;
+      const float miv_f = mean_f * iv_f;
+      div_[(size_t)c * D + i] = iv_f;
+      dmiv[(size_t)c * D + i] = miv_f;
+      gc += 0.5 * log((double)iv_f) - 0.5 * (double)miv_f * (double)miv_f / (double)iv_f;
+    }
+    dgc[c] = (float)gc;
+  }
+  if ((rcode = fb_load_diag_gmm(ctx, 0, dw.data(), dmiv.data(), div_.data(), dgc.data(), C, D))) return rcode;
+  if ((rcode = fb_finalize_gmms(ctx, 1))) return rcode;
+  v->have_ubm = true;
+  return FB_OK;
+}
+
+extern "C" int fb_load_ivector_extractor(fb_ctx *ctx, const double *M, const double *sigma_inv, double prior_offset, int C, int D,
+                                         int R) {
+  FB_CHECK_ARG(ctx && M && sigma_inv, "NULL argument");
+  FB_CHECK_ARG(D == FB_DIM, "feature dimension must be 72");
+  FB_CHECK_ARG(R >= 2 && R <= 512, "i-vector dimension must be in [2, 512]");
+  FB_CUDA(cudaSetDevice(ctx->device));
+  FbIvector *v = iv_get(ctx);
+  FB_CHECK_ARG(!v->have_ubm || v->C == C, "extractor and full UBM disagree on the number of components");
+  v->C = C;
+  v->R = R;
+  v->n_packed = R * (R + 1) / 2;
+  v->prior_offset = prior_offset;
+  double *dM = nullptr, *dS = nullptr, *dSim = nullptr;
+  const size_t nM = (size_t)C * D * R, nS = (size_t)C * D * D;
+  FB_CUDA(cudaMalloc(&dM, nM * sizeof(double)));
+  FB_CUDA(cudaMalloc(&dS, nS * sizeof(double)));
+  FB_CUDA(cudaMalloc(&dSim, nM * sizeof(double)));
+  FB_CUDA(cudaMemcpy(dM, M, nM * sizeof(double), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(dS, sigma_inv, nS * sizeof(double), cudaMemcpyHostToDevice));
+  int rc;
+  if ((rc = v->sim32.ensure(nM))) return rc;
+  if ((rc = v->U.ensure((size_t)C * v->n_packed))) return rc;
+  ivec_derive_sim_kernel<<<C, 256, 0, ctx->stream>>>(dM, dS, R, dSim, v->sim32.p);
+  ivec_derive_u_kernel<<<dim3(fb_div_up(v->n_packed, 256), C), 256, 0, ctx->stream>>>(dM, dSim, R, v->n_packed, v->U.p);
+  FB_CUDA(cudaGetLastError());
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dM); cudaFree(dS); cudaFree(dSim);
+  v->have_ie = true;
+  return FB_OK;
+}
+
+// Plda::TransformIvector (normalize_length, num_examples = 1) on the host, float64
+static void plda_transform_host(const FbIvector *v, const float *raw, double *out) {
+  const int R = v->R, L = v->L;
+  std::vector<float> c(R), t(L);
+  for (int r = 0; r < R; ++r) c[r] = raw[r] - v->h_mean_vec[r];
+  for (int l = 0; l < L; ++l) {
+    float acc = (v->lda_cols == R + 1) ? v->h_lda[(size_t)l * v->lda_cols + R] : 0.f;
+    for (int r = 0; r < R; ++r) acc += v->h_lda[(size_t)l * v->lda_cols + r] * c[r];
+    t[l] = acc;
+  }
+  double tot = 0.0;
+  for (int l = 0; l < L; ++l) tot += (double)t[l] * (double)t[l];
+  const float ratio = (float)sqrt(tot) / sqrtf((float)L);
+  const float inv_ratio = 1.0f / ratio;
+  for (int l = 0; l < L; ++l) t[l] *= inv_ratio;
+  double dot = 0.0;
+  for (int l = 0; l < L; ++l) {
+    double acc = v->h_plda_off[l];
+    for (int k = 0; k < L; ++k) acc += v->h_plda_T[(size_t)l * L + k] * (double)t[k];
+    out[l] = acc;
+    dot += acc * acc / (v->h_psi[l] + 1.0);
+  }
+  const double f = sqrt((double)L / dot);
+  for (int l = 0; l < L; ++l) out[l] *= f;
+}
+
+extern "C" int fb_load_plda_backend(fb_ctx *ctx, const float *mean_vec, const float *transform_mat, int transform_cols,
+                                    const double *plda_mean, const double *plda_transform, const double *plda_psi, int R, int L) {
+  FB_CHECK_ARG(ctx && mean_vec && transform_mat && plda_mean && plda_transform && plda_psi, "NULL argument");
+  FB_CHECK_ARG(transform_cols == R || transform_cols == R + 1, "transform.mat must have R or R+1 columns");
+  FB_CHECK_ARG(L >= 1 && L <= 512, "PLDA dimension must be in [1, 512]");
+  FB_CUDA(cudaSetDevice(ctx->device));
+  FbIvector *v = iv_get(ctx);
+  FB_CHECK_ARG(!v->have_ie || v->R == R, "back-end and extractor disagree on the i-vector dimension");
+  v->R = R;
+  v->L = L;
+  v->lda_cols = transform_cols;
+  v->h_mean_vec.assign(mean_vec, mean_vec + R);
+  v->h_lda.assign(transform_mat, transform_mat + (size_t)L * transform_cols);
+  v->h_plda_T.assign(plda_transform, plda_transform + (size_t)L * L);
+  v->h_psi.assign(plda_psi, plda_psi + L);
+  v->h_plda_off.assign(L, 0.0);
+  for (int l = 0; l < L; ++l) {
+    double acc = 0.0;
+    for (int k = 0; k < L; ++k) acc += plda_transform[(size_t)l * L + k] * plda_mean[k];
+    v->h_plda_off[l] = -acc;
+  }
+  int rc;
+  if ((rc = v->mean_vec.ensure(R))) return rc;
+  if ((rc = v->lda.ensure(v->h_lda.size()))) return rc;
+  if ((rc = v->plda_T.ensure(v->h_plda_T.size()))) return rc;
+  if ((rc = v->plda_off.ensure(L))) return rc;
+  if ((rc = v->psi.ensure(L))) return rc;
+  FB_CUDA(cudaMemcpy(v->mean_vec.p, mean_vec, R * sizeof(float), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(v->lda.p, v->h_lda.data(), v->h_lda.size() * sizeof(float), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(v->plda_T.p, v->h_plda_T.data(), v->h_plda_T.size() * sizeof(double), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(v->plda_off.p, v->h_plda_off.data(), L * sizeof(double), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(v->psi.p, v->h_psi.data(), L * sizeof(double), cudaMemcpyHostToDevice));
+  v->have_backend = true;
+  return FB_OK;
+}
+
+extern "C" int fb_set_enrolled_ivectors(fb_ctx *ctx, const float *enrolled, int K) {
+  FB_CHECK_ARG(ctx && enrolled && K >= 1 && K < FB_MAX_MODELS, "bad argument");
+  FbIvector *v = ctx->iv;
+  FB_CHECK_ARG(v && v->have_backend, "fb_load_plda_backend must be called first");
+  FB_CUDA(cudaSetDevice(ctx->device));
+  std::vector<double> u((size_t)K * v->L);
+  for (int k = 0; k < K; ++k) plda_transform_host(v, enrolled + (size_t)k * v->R, u.data() + (size_t)k * v->L);
+  int rc;
+  if ((rc = v->u_train.ensure(u.size()))) return rc;
+  FB_CUDA(cudaMemcpy(v->u_train.p, u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice));
+  v->K = K;
+  ctx->arch = 1;
+  return FB_OK;
+}
+
+static int iv_reserve(fb_ctx *ctx) {
+  FbIvector *v = ctx->iv;
+  const int B = ctx->B;
+  int rc;
+  if ((rc = v->ll.ensure((size_t)ctx->rows_cap * v->C))) return rc;
+  if ((rc = v->gsel.ensure((size_t)ctx->rows_cap * IV_NSEL))) return rc;
+  if ((rc = v->post.ensure((size_t)ctx->rows_cap * IV_NSEL))) return rc;
+  if ((rc = v->gamma.ensure((size_t)B * v->C))) return rc;
+  if ((rc = v->Xs.ensure((size_t)B * v->C * FB_DIM))) return rc;
+  v->n_splits = ctx->num_sms < v->C ? ctx->num_sms : v->C;
+  if ((rc = v->lin_part.ensure((size_t)v->n_splits * B * v->R))) return rc;
+  if ((rc = v->quad.ensure((size_t)B * v->n_packed))) return rc;
+  if ((rc = v->Awork.ensure((size_t)B * v->R * v->R))) return rc;
+  if ((rc = v->ivec.ensure((size_t)B * v->R))) return rc;
+  if ((rc = v->scores.ensure((size_t)B * (v->K > 0 ? v->K : 1)))) return rc;
+  return FB_OK;
+}
+
+// i-vectors (and, when speakers are enrolled, PLDA scores) for the batch whose features are in the context.
+int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
+  FbIvector *v = ctx->iv;
+  FB_CHECK_ARG(v && v->have_ubm && v->have_ie, "full UBM and i-vector extractor must be loaded");
+  FB_CHECK_ARG(!with_plda || (v->have_backend && v->K > 0), "PLDA back-end / enrolled speakers missing");
+  int rc;
+  if ((rc = iv_reserve(ctx))) return rc;
+  const int B = ctx->B;
+  const int rows = ctx->total_frames;           // upper bound of the voiced rows (device knows the exact count)
+  if ((rc = fb_run_gmm_store(ctx, v->ll.p, done_flag))) return rc;
+  gselect_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(v->ll.p, ctx->misc.p, v->C, v->gsel.p, done_flag);
+  fgmm_post_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->gconsts.p, v->means_invcovars.p,
+                                                                  v->inv_covars.p, v->rc_table.p, ctx->misc.p, v->min_post, v->post.p,
+                                                                  done_flag);
+  const int max_pairs = ctx->max_frames * IV_NSEL;
+  const size_t smem_stats = (size_t)(3 * v->C + 1) * sizeof(int) + (size_t)(2 * max_pairs + 2) * sizeof(unsigned short) +
+                            (size_t)2 * max_pairs * sizeof(float) + 16;
+  if (smem_stats > 220 * 1024) {
+    fb_set_error("utterance of %d frames is too long for the i-vector statistics kernel (limit ~%d frames)", ctx->max_frames,
+                 (int)((220 * 1024 - 3 * v->C * 4) / (IV_NSEL * 12)));
+    return FB_ERR_UNSUPPORTED;
+  }
+  static bool attr = false;
+  if (!attr) {
+    FB_CUDA(cudaFuncSetAttribute(ivec_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr = true;
+  }
+  ivec_stats_kernel<<<B, 256, smem_stats, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->post.p, ctx->row_off.p, v->C, max_pairs,
+                                                         v->gamma.p, v->Xs.p, ctx->misc.p + 1, done_flag);
+  const int bch = fb_div_up(B, IV_BCHUNK);
+  const int lin_threads = ((v->R + 31) / 32) * 32;
+  ivec_lin_kernel<<<dim3(v->n_splits, bch), lin_threads, 0, ctx->stream>>>(v->sim32.p, v->Xs.p, v->gamma.p, B, v->C, v->R,
+                                                                          v->n_splits, v->lin_part.p, done_flag);
+  ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, B, v->C, v->n_packed,
+                                                                                   v->quad.p, done_flag);
+  ivec_solve_kernel<<<B, 512, 2 * v->R * sizeof(double), ctx->stream>>>(v->quad.p, v->lin_part.p, v->n_splits, B, v->R, v->n_packed,
+                                                                        v->prior_offset, v->Awork.p, v->ivec.p, ctx->misc.p + 1,
+                                                                        done_flag);
+  ctx->launches += 6;
+  if (with_plda) {
+    const size_t smem_plda = (size_t)v->L * sizeof(double) + (size_t)(v->R + v->L) * sizeof(float) + 16;
+    plda_kernel<<<B, 256, smem_plda, ctx->stream>>>(v->ivec.p, v->mean_vec.p, v->lda.p, v->lda_cols, v->plda_T.p, v->plda_off.p,
+                                                    v->psi.p, v->u_train.p, v->R, v->L, v->K, v->scores.p, done_flag);
+    ctx->launches += 1;
+  }
+  fb_prof_mark(ctx, 5);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+static int iv_check(fb_ctx *ctx) {
+  int misc[3];
+  FB_CUDA(cudaMemcpyAsync(misc, ctx->misc.p, sizeof(misc), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (misc[1] != 0) {
+    const int zero = 0;
+    cudaMemcpy(ctx->misc.p + 1, &zero, sizeof(int), cudaMemcpyHostToDevice);
+    if (misc[1] == 2) fb_set_error("utterance too long for the i-vector statistics kernel");
+    else if (misc[1] == 3) fb_set_error("i-vector posterior precision matrix is not positive definite");
+    else { fb_set_error("utterance %d has no voiced frames", misc[1] - 16); return FB_ERR_NO_VOICED; }
+    return FB_ERR_STATE;
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_score_ivector_host(fb_ctx *ctx, const int16_t *wave, const int64_t *offsets, int B, double *out_scores,
+                                     float *out_ivectors) {
+  FB_CHECK_ARG(ctx && wave && offsets, "NULL argument");
+  FB_CHECK_ARG(offsets[0] == 0, "offsets[0] must be 0");
+  FbIvector *v = ctx->iv;
+  FB_CHECK_ARG(v && v->have_ubm && v->have_ie, "full UBM and i-vector extractor must be loaded");
+  FB_CHECK_ARG(!out_scores || (v->have_backend && v->K > 0), "PLDA back-end / enrolled speakers missing");
+  FB_CUDA(cudaSetDevice(ctx->device));
+  int rc;
+  ctx->need_feats_f32 = true;
+  if ((rc = fb_prepare_tables(ctx))) return rc;
+  if ((rc = fb_reserve_batch(ctx, B, offsets))) return rc;
+  ctx->batch_tag = 0;
+  if ((rc = ctx->wave.ensure((size_t)offsets[B] + 8))) return rc;
+  FB_CUDA(cudaMemcpyAsync(ctx->wave.p, wave, (size_t)offsets[B] * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  fb_prof_mark(ctx, -1);
+  if ((rc = fb_run_frontend_flag(ctx, nullptr))) return rc;
+  if ((rc = fb_run_ivector_flag(ctx, nullptr, out_scores != nullptr))) return rc;
+  if (out_scores)
+    FB_CUDA(cudaMemcpyAsync(out_scores, v->scores.p, (size_t)B * v->K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_ivectors)
+    FB_CUDA(cudaMemcpyAsync(out_ivectors, v->ivec.p, (size_t)B * v->R * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  return iv_check(ctx);
+}
+
+extern "C" int fb_get_posteriors(fb_ctx *ctx, int32_t *gsel_host, float *post_host, int64_t capacity_rows) {
+  FB_CHECK_ARG(ctx && ctx->iv && gsel_host && post_host, "bad argument");
+  int misc[3];
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  FB_CUDA(cudaMemcpy(misc, ctx->misc.p, sizeof(misc), cudaMemcpyDeviceToHost));
+  const int rows = misc[2];
+  FB_CHECK_ARG(capacity_rows >= rows, "output buffers too small");
+  FB_CUDA(cudaMemcpy(gsel_host, ctx->iv->gsel.p, (size_t)rows * IV_NSEL * sizeof(int), cudaMemcpyDeviceToHost));
+  FB_CUDA(cudaMemcpy(post_host, ctx->iv->post.p, (size_t)rows * IV_NSEL * sizeof(float), cudaMemcpyDeviceToHost));
+  return rows;
+}

@@ -14,6 +14,7 @@
 // (no FMA contraction), so given identical losses and noise the update is bit-identical to numpy.
 #include "fb_common.cuh"
 #include "fb_nes.cuh"
+#include "fb_ivector.cuh"
 #include <math.h>
 #include <string.h>
 
@@ -130,7 +131,7 @@ __device__ double sample_loss(const FbNesDev &st, const double *ll) {
   double sc_own = 0.0, sc_other = -INFINITY, sc_max = -INFINITY;
   for (int k = 0; k < K; ++k) {
     double s;
-    if (st.task == FB_TASK_CSI) s = __ddiv_rn(__dadd_rn(ll[k], -st.zmean[k]), st.zstd[k]);
+    if (st.znorm) s = __ddiv_rn(__dadd_rn(ll[k], -st.zmean[k]), st.zstd[k]);
     else s = __dadd_rn(ll[1 + k], -ll[0]);
     if (k == st.label) sc_own = s; else sc_other = fmax(sc_other, s);
     sc_max = fmax(sc_max, s);
@@ -210,7 +211,7 @@ nes_loss_kernel(FbNesDev st, const double *__restrict__ avg_ll, int n_models, in
     if (col == 0) {
       for (int k = 0; k < st.K; ++k) {
         double s;
-        if (st.task == FB_TASK_CSI) s = __ddiv_rn(__dadd_rn(ll[k], -st.zmean[k]), st.zstd[k]);
+        if (st.znorm) s = __ddiv_rn(__dadd_rn(ll[k], -st.zmean[k]), st.zstd[k]);
         else s = __dadd_rn(ll[1 + k], -ll[0]);
         st.red[st.N + st.S + 1 + k] = s;
       }
@@ -323,6 +324,7 @@ __global__ void nes_init_kernel(FbNesDev st) {
 static int nes_claim_batch(fb_ctx *ctx) {
   FbNes *s = ctx->nes;
   int rc;
+  if (ctx->arch == 1) ctx->need_feats_f32 = true;
   if (ctx->batch_tag != 1) {
     if ((rc = ctx->wave.ensure((size_t)s->B_local * s->N + 8))) return rc;
     if ((rc = fb_reserve_batch(ctx, s->B_local, s->offsets.data()))) return rc;
@@ -364,8 +366,14 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   FB_CHECK_ARG(p->plateau_length >= 1 && p->plateau_length <= 64, "plateau_length must be in [1,64]");
   FB_CHECK_ARG(p->max_iter >= 1, "max_iter must be >= 1");
   const int K = p->n_speakers;
-  const int need_models = (p->task == FB_TASK_CSI) ? K : K + 1;
-  FB_CHECK_ARG(ctx->n_models == need_models, "loaded model slots do not match task / n_speakers");
+  const bool iv = ctx->arch == 1;
+  if (iv) {
+    FB_CHECK_ARG(ctx->iv && ctx->iv->K == K, "enrolled i-vectors do not match n_speakers");
+    FB_CHECK_ARG(p->z_norm_means && p->z_norm_stds, "i-vector scorers need z-norm statistics");
+  } else {
+    const int need_models = (p->task == FB_TASK_CSI) ? K : K + 1;
+    FB_CHECK_ARG(ctx->n_models == need_models, "loaded model slots do not match task / n_speakers");
+  }
   if (p->task == FB_TASK_SV) FB_CHECK_ARG(K == 1, "SV needs exactly one speaker");
   if (p->task == FB_TASK_CSI || (p->task == FB_TASK_OSI && p->targeted)) {
     FB_CHECK_ARG(K >= 2, "this loss needs at least two speakers");
@@ -418,13 +426,14 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   d.dist_bits = s->dist_bits;
   d.N = n_samples; d.S = S; d.K = K; d.pairs_total = pairs_total; d.pairs_local = s->pairs_local; d.pair0 = p0;
   d.B_local = s->B_local; d.has_clean = s->has_clean ? 1 : 0;
+  d.znorm = (iv || p->task == FB_TASK_CSI) ? 1 : 0;
   d.task = p->task; d.targeted = p->targeted; d.label = p->label; d.plateau_length = p->plateau_length;
   d.auto_stop = 1;
   d.kappa = p->adver_thresh; d.sigma = p->sigma; d.epsilon = p->epsilon; d.momentum = p->momentum;
   d.one_minus_momentum = 1.0 - p->momentum;
   d.min_lr = p->min_lr; d.plateau_drop = p->plateau_drop; d.seed = p->seed;
   FB_CUDA(cudaMemcpyAsync(d.audio, audio_host, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (p->task == FB_TASK_CSI) {
+  if (d.znorm) {
     FB_CUDA(cudaMemcpyAsync(d.zmean, p->z_norm_means, K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(d.zstd, p->z_norm_stds, K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
@@ -455,13 +464,23 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
   fb_prof_mark(ctx, 0);
   ctx->launches += 1;
   if ((rc = fb_run_frontend_flag(ctx, d.flags))) return rc;
-  if ((rc = fb_run_gmm_flag(ctx, d.flags))) return rc;
+  const double *ll_dev;
+  int ll_stride;
+  if (ctx->arch == 1) {
+    if ((rc = fb_run_ivector_flag(ctx, d.flags, true))) return rc;
+    ll_dev = ctx->iv->scores.p;
+    ll_stride = ctx->iv->K;
+  } else {
+    if ((rc = fb_run_gmm_flag(ctx, d.flags))) return rc;
+    ll_dev = ctx->avg_ll.p;
+    ll_stride = ctx->n_models;
+  }
   const int multi = s->world > 1;
   if (multi) {
     nes_zero_red_kernel<<<1, 256, 0, ctx->stream>>>(d);
     ctx->launches += 1;
   }
-  nes_loss_kernel<<<1, 256, 0, ctx->stream>>>(d, ctx->avg_ll.p, ctx->n_models, mode_get_grad ? 2 : (multi ? 0 : 1));
+  nes_loss_kernel<<<1, 256, 0, ctx->stream>>>(d, ll_dev, ll_stride, mode_get_grad ? 2 : (multi ? 0 : 1));
   fb_prof_mark(ctx, 6);
   ctx->launches += 1;
   const int nb = fb_div_up(s->N, 128);
@@ -530,7 +549,7 @@ extern "C" int fb_nes_status(fb_ctx *ctx, int *iters_done, int *stopped) {
   int err[2];
   FB_CUDA(cudaMemcpy(err, ctx->misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost));
   if (err[0] != 0) {
-    fb_set_error("utterance %d of the NES batch has no voiced frames", err[0] - 1);
+    fb_set_error("NES batch failed on device (code %d: >=16 utterance without voiced frames, 2 utterance too long, 3 matrix not SPD)", err[0]);
     return FB_ERR_NO_VOICED;
   }
   if (iters_done) *iters_done = h[1];
@@ -591,7 +610,7 @@ extern "C" int fb_nes_get_grad(fb_ctx *ctx, const double *noise_host, double *fi
   FB_CUDA(cudaStreamSynchronize(ctx->stream));
   int err = 0;
   FB_CUDA(cudaMemcpy(&err, ctx->misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err != 0) { fb_set_error("utterance %d of the NES batch has no voiced frames", err - 1); return FB_ERR_NO_VOICED; }
+  if (err != 0) { fb_set_error("NES batch failed on device (code %d)", err); return FB_ERR_NO_VOICED; }
   if (adver_loss) *adver_loss = tail[0];
   if (final_loss) {
     // np.mean(loss[1:]) in numpy's pairwise order, on the host

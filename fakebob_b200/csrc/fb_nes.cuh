@@ -16,7 +16,7 @@ struct FbNesDev {
   unsigned long long *dist_bits;   // [iter] L-inf distance before iteration `iter` (as double bits)
   int64_t N;
   int S, K, pairs_total, pairs_local, pair0, B_local, has_clean;
-  int task, targeted, label, plateau_length, auto_stop;
+  int task, targeted, label, plateau_length, auto_stop, znorm;
   double kappa, sigma, epsilon, momentum, one_minus_momentum, min_lr, plateau_drop;
   unsigned long long seed;
 };

@@ -259,3 +259,85 @@ class GmmEngine:
         dist.broadcast_object_list(obj, src=0)
         ident = (C.c_char * 128).from_buffer_copy(obj[0])
         _lib.check(self.lib.fb_comm_init(self.h, ident, rank, world))
+
+
+class IvectorEngine(GmmEngine):
+    """Resident full UBM + i-vector extractor + LDA/PLDA back-end on one B200 (replaces ivector_PLDA_kaldiHelper)."""
+
+    def __init__(self, pre_model_dir, feat_cfg=None, device=None):
+        self.lib = _lib.load()
+        self.device = default_device() if device is None else device
+        self.cfg = feat_cfg or FeatureConfig()
+        self.cfg.check_supported()
+        h = C.c_void_p()
+        _lib.check(self.lib.fb_ctx_create(self.device, C.byref(h)))
+        self.h = h
+        fc = _lib.FeatConfig(self.cfg.sample_frequency, self.cfg.low_freq, self.cfg.high_freq, self.cfg.num_mel_bins,
+                             self.cfg.num_ceps, self.cfg.preemph, self.cfg.cepstral_lifter,
+                             self.cfg.vad_energy_threshold, self.cfg.vad_energy_mean_scale,
+                             self.cfg.vad_proportion_threshold, self.cfg.vad_frames_context, self.cfg.cmn_window)
+        _lib.check(self.lib.fb_set_feature_config(self.h, C.byref(fc)))
+        pre = pre_model_dir
+        fg = kaldi_io.read_full_gmm(os.path.join(pre, "final.ubm"))
+        w = np.ascontiguousarray(fg["weights"], dtype=np.float32)
+        mic = np.ascontiguousarray(fg["means_invcovars"], dtype=np.float32)
+        ic = np.ascontiguousarray(fg["inv_covars"], dtype=np.float32)
+        gc = np.ascontiguousarray(fg["gconsts"], dtype=np.float32)
+        Cn, D = mic.shape
+        _lib.check(self.lib.fb_load_full_gmm(self.h, _ptr(w), _ptr(mic), _ptr(ic), _ptr(gc), Cn, D))
+        ie = kaldi_io.read_ivector_extractor(os.path.join(pre, "final.ie"))
+        if ie["w"].size:
+            raise ValueError("i-vector extractors with weight projection (<w> non-empty) are not supported")
+        M = np.ascontiguousarray(ie["M"], dtype=np.float64)
+        S = np.ascontiguousarray(ie["sigma_inv"], dtype=np.float64)
+        self.R = M.shape[2]
+        _lib.check(self.lib.fb_load_ivector_extractor(self.h, _ptr(M), _ptr(S), float(ie["prior_offset"]), Cn, D, self.R))
+        mean_vec = np.ascontiguousarray(kaldi_io.read_vector(os.path.join(pre, "mean.vec")), dtype=np.float32)
+        tm = np.ascontiguousarray(kaldi_io.read_matrix(os.path.join(pre, "transform.mat")), dtype=np.float32)
+        pl = kaldi_io.read_plda(os.path.join(pre, "plda"))
+        self.L = tm.shape[0]
+        _lib.check(self.lib.fb_load_plda_backend(self.h, _ptr(mean_vec), _ptr(tm), tm.shape[1],
+                                                 _ptr(np.ascontiguousarray(pl["mean"])), _ptr(np.ascontiguousarray(pl["transform"])),
+                                                 _ptr(np.ascontiguousarray(pl["psi"])), self.R, self.L))
+        self.n_models = 1
+        self.K = 0
+        self._nes_keep = None
+        self._last_B = 0
+
+    def set_enrolled(self, ivectors):
+        e = np.ascontiguousarray(np.atleast_2d(ivectors), dtype=np.float32)
+        _lib.check(self.lib.fb_set_enrolled_ivectors(self.h, _ptr(e), e.shape[0]))
+        self.K = e.shape[0]
+
+    def _pack(self, audio_list):
+        B = len(audio_list)
+        lens = np.array([a.shape[0] for a in audio_list], dtype=np.int64)
+        offsets = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        wave = np.ascontiguousarray(np.concatenate(audio_list) if B > 1 else audio_list[0], dtype=np.int16)
+        return wave, offsets, B
+
+    def extract_ivectors(self, audio_list):
+        """list of int16 arrays -> (B, R) float32 raw i-vectors (what ivector-extract writes)."""
+        wave, offsets, B = self._pack(audio_list)
+        out = np.empty((B, self.R), dtype=np.float32)
+        _lib.check(self.lib.fb_score_ivector_host(self.h, _ptr(wave), _ptr(offsets), B, None, _ptr(out)))
+        self._last_B = B
+        return out
+
+    def score_plda(self, audio_list, want_ivectors=False):
+        """-> (B, K) float64 PLDA log-likelihood ratios against the enrolled speakers."""
+        wave, offsets, B = self._pack(audio_list)
+        out = np.empty((B, self.K), dtype=np.float64)
+        iv = np.empty((B, self.R), dtype=np.float32) if want_ivectors else None
+        _lib.check(self.lib.fb_score_ivector_host(self.h, _ptr(wave), _ptr(offsets), B, _ptr(out), _ptr(iv) if iv is not None else None))
+        self._last_B = B
+        return (out, iv) if want_ivectors else out
+
+    def posteriors(self):
+        """Gaussian selection and pruned posteriors of the last batch: (rows, 20) int32 / float32."""
+        rows = self.voiced_rows()
+        g = np.empty((rows, 20), dtype=np.int32)
+        p = np.empty((rows, 20), dtype=np.float32)
+        _lib.check(self.lib.fb_get_posteriors(self.h, _ptr(g), _ptr(p), rows))
+        return g, p

@@ -222,7 +222,7 @@ def build_ivector_params(root, ubm_params, R=400, L=200, seed=11, rank=4):
         gconsts[c] = np.log(w[c]) - 0.5 * (D * np.log(2 * np.pi) + logdet + mu[c] @ ic @ mu[c])
     kaldi_io.write_full_gmm(os.path.join(pre_dir, "final.ubm"), w, means_invcovars, inv_covars, gconsts)
     prior_offset = 100.0
-    M = r.standard_normal((C, D, R)) * 0.05 * sd[:, :, None]
+    M = r.standard_normal((C, D, R)) * 0.3 * sd[:, :, None]
     M[:, :, 0] = mu / prior_offset
     # Kaldi stores Sigma_inv as float64 SpMatrix; derive from the float32-rounded full UBM like a real run
     sig_inv = inv_covars.astype(np.float32).astype(np.float64)

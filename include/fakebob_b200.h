@@ -82,6 +82,26 @@ int fb_set_gmm_impl(fb_ctx *ctx, int impl);
 int fb_score_gmm_host(fb_ctx *ctx, const int16_t *wave, const int64_t *offsets, int B, double *out_avg_ll);
 int fb_score_gmm_dev(fb_ctx *ctx, const int16_t *wave_dev, const int64_t *offsets_host, int B, double *out_avg_ll_dev);
 
+/* ---- i-vector / PLDA scoring: serves iv_{CSI,OSI,SV}.score() ---------------------------------
+ * Replaces: ivector_PLDA_kaldiHelper.score() (ivector_PLDA_kaldiHelper.py:340-363): write_audio, data_prepare, make_mfcc,
+ * compute_vad, extract_ivector (sid/extract_ivectors.sh, :202-211), write_trials, plda_scoring (:251-280), resolve_score.
+ * Parameters are Kaldi's stored members: final.ubm (FullGmm: inv_covars as full symmetric C x D x D float32),
+ * final.ie (M: C x D x R, SigmaInv: C x D x D, float64; no weight projection), mean.vec, transform.mat (L x R or
+ * L x (R+1)), plda (mean, transform, psi; float64).  Derived matrices are computed once, on the device. */
+int fb_load_full_gmm(fb_ctx *ctx, const float *weights, const float *means_invcovars, const float *inv_covars,
+                     const float *gconsts, int C, int D);
+int fb_load_ivector_extractor(fb_ctx *ctx, const double *M, const double *sigma_inv, double prior_offset, int C, int D, int R);
+int fb_load_plda_backend(fb_ctx *ctx, const float *mean_vec, const float *transform_mat, int transform_cols,
+                         const double *plda_mean, const double *plda_transform, const double *plda_psi, int R, int L);
+/* Raw enrolled i-vectors (K x R float32, as read from the pickle's identity_location); back-end applied on load. */
+int fb_set_enrolled_ivectors(fb_ctx *ctx, const float *enrolled, int K);
+/* out_scores[b * K + k] = PLDA log-likelihood ratio of test utterance b against enrolled speaker k (float64; what
+ * ivector-plda-scoring prints), or NULL; out_ivectors[b * R + r] = raw i-vectors (what ivector-extract writes), or NULL. */
+int fb_score_ivector_host(fb_ctx *ctx, const int16_t *wave, const int64_t *offsets, int B, double *out_scores,
+                          float *out_ivectors);
+/* Gaussian selection and pruned posteriors of the last i-vector batch: [rows][20] each; returns rows. */
+int fb_get_posteriors(fb_ctx *ctx, int32_t *gsel_host, float *post_host, int64_t capacity_rows);
+
 /* ---- stage read-backs (used by the parity tests; valid after a score call) ------------ */
 int fb_set_debug(fb_ctx *ctx, int keep_f32_features);
 int fb_get_num_frames(fb_ctx *ctx, int B, int32_t *frames_host, int32_t *voiced_host);

@@ -59,3 +59,17 @@ def small_oracle_models(small_tree):
 def test_audio(seed, spk=0, n=32000):
     from fakebob_b200 import synth
     return synth.synth_utterance(seed=seed, spk_seed=spk, n_samples=n)
+
+
+@pytest.fixture(scope="session")
+def small_iv_tree(small_tree):
+    """Adds final.ubm / final.ie / mean.vec / transform.mat / plda and enrolled speakers (*.iv pickles) to small_tree."""
+    from fakebob_b200 import synth
+    from oracle.ivector import load_system
+    root = small_tree["root"]
+    synth.build_ivector_params(root, small_tree["ubm_params"], R=40, L=20)
+    system = load_system(small_tree["pre_model_dir"])
+    spk = synth.build_ivector_speakers(root, system.extract, system.plda_scores, n_speakers=3, n_samples=32000, n_znorm_utts=4)
+    out = dict(small_tree)
+    out.update(iv_models=spk["models"], enrolled=spk["enrolled"], system=system)
+    return out
