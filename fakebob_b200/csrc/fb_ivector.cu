@@ -252,100 +252,153 @@ ivec_derive_u_kernel(const double *__restrict__ M, const double *__restrict__ si
 }
 
 // ------------------------------------------------------------------------------------------------
-// lin partials: each CTA owns a contiguous range of components and all R columns; thread r accumulates IV_BCHUNK
-// utterances in float64 registers.  grid (n_splits, ceil(B / IV_BCHUNK)), block = R rounded up to 32.
+// lin and quad: float64 accumulation of fp32 parameter streams, register-tiled: each thread owns 4 consecutive output
+// columns x 8 utterances (32 accumulators); parameters come in as one float4 per thread per k, statistics as 4 LDS.128.
+// A CTA covers IV_BCHUNK = 32 utterances; components whose gamma is zero for all 32 utterances are skipped entirely
+// (NES batches are perturbations of one audio, so their active component sets nearly coincide).
 // ------------------------------------------------------------------------------------------------
 #define IV_BCHUNK 32
 
+// lin partials: grid (n_splits, ceil(B/32)); block = 4 utterance-groups x ceil(R/4) column-groups (R <= 512).
 __global__ void __launch_bounds__(512)
 ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, const double *__restrict__ gamma, int B, int C,
                 int R, int n_splits, double *__restrict__ part, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  __shared__ double s_x[IV_BCHUNK][FB_DIM];
-  __shared__ int s_act[IV_BCHUNK];
+  __shared__ __align__(16) double s_x[FB_DIM][IV_BCHUNK];
+  __shared__ int s_any;
   const int split = blockIdx.x;
   const int b0 = blockIdx.y * IV_BCHUNK;
   const int nb = min(IV_BCHUNK, B - b0);
   const int c0 = (int)((long long)C * split / n_splits), c1 = (int)((long long)C * (split + 1) / n_splits);
-  const int r = threadIdx.x;
-  double acc[IV_BCHUNK];
+  const int ncg = (R + 3) / 4;
+  const int ug = threadIdx.x / ncg, cg = threadIdx.x - ug * ncg;      // utterance group 0..3, column group
+  const bool active = ug < 4;
+  const int r0 = cg * 4;
+  double acc[4][8];
 #pragma unroll
-  for (int i = 0; i < IV_BCHUNK; ++i) acc[i] = 0.0;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
   for (int c = c0; c < c1; ++c) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nb * FB_DIM; idx += blockDim.x) {
-      const int i = idx / FB_DIM, d = idx - i * FB_DIM;
-      s_x[i][d] = Xs[((size_t)(b0 + i) * C + c) * FB_DIM + d];
-    }
-    if (threadIdx.x < nb) s_act[threadIdx.x] = gamma[(size_t)(b0 + threadIdx.x) * C + c] != 0.0;
+    if (threadIdx.x == 0) s_any = 0;
     __syncthreads();
-    if (r < R) {
-      const float *col = sim32 + (size_t)c * FB_DIM * R + r;
-      for (int d = 0; d < FB_DIM; ++d) {
-        const double sv = (double)col[(size_t)d * R];
+    if (threadIdx.x < nb && gamma[(size_t)(b0 + threadIdx.x) * C + c] != 0.0) s_any = 1;
+    for (int idx = threadIdx.x; idx < FB_DIM * IV_BCHUNK; idx += blockDim.x) {
+      const int d = idx / IV_BCHUNK, i = idx - d * IV_BCHUNK;
+      s_x[d][i] = (i < nb) ? Xs[((size_t)(b0 + i) * C + c) * FB_DIM + d] : 0.0;
+    }
+    __syncthreads();
+    if (!s_any || !active) continue;
+    const float *col = sim32 + (size_t)c * FB_DIM * R + r0;
+    for (int d = 0; d < FB_DIM; ++d) {
+      float p[4];
+      if (r0 + 3 < R && (R & 3) == 0) {
+        const float4 q = *reinterpret_cast<const float4 *>(col + (size_t)d * R);
+        p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
+      } else {
 #pragma unroll
-        for (int i = 0; i < IV_BCHUNK; ++i)
-          if (i < nb && s_act[i]) acc[i] += sv * s_x[i][d];
+        for (int i = 0; i < 4; ++i) p[i] = (r0 + i < R) ? col[(size_t)d * R + i] : 0.f;
       }
+      const double2 *xr = reinterpret_cast<const double2 *>(&s_x[d][ug * 8]);
+      const double2 x01 = xr[0], x23 = xr[1], x45 = xr[2], x67 = xr[3];
+      const double x[8] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y, x67.x, x67.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += (double)p[i] * x[j];
     }
   }
-  if (r < R)
+  if (active)
 #pragma unroll
-    for (int i = 0; i < IV_BCHUNK; ++i)
-      if (i < nb) part[((size_t)split * B + b0 + i) * R + r] = acc[i];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = r0 + i, bi = ug * 8 + j;
+        if (r < R && bi < nb) part[((size_t)split * B + b0 + bi) * R + r] = acc[i][j];
+      }
 }
 
-// quad: thread = packed entry e; accumulates IV_BCHUNK utterances; gamma staged through shared memory in chunks.
-// grid (ceil(n_packed / 256), ceil(B / IV_BCHUNK)).
+// quad: grid (ceil(n_packed / 256), ceil(B/32)); block 256 = 4 utterance-groups x 64 column-groups of 4 packed entries.
 __global__ void __launch_bounds__(256)
 ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, int B, int C, int n_packed,
                  double *__restrict__ quad, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  __shared__ double s_g[IV_BCHUNK][128];
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ __align__(16) double s_g[64][IV_BCHUNK];
+  __shared__ int s_any[64];
   const int b0 = blockIdx.y * IV_BCHUNK;
   const int nb = min(IV_BCHUNK, B - b0);
-  double acc[IV_BCHUNK];
+  const int ug = threadIdx.x >> 6, cg = threadIdx.x & 63;
+  const int e0 = blockIdx.x * 256 + cg * 4;
+  const bool vec_ok = (n_packed & 3) == 0 && e0 + 3 < n_packed;
+  double acc[4][8];
 #pragma unroll
-  for (int i = 0; i < IV_BCHUNK; ++i) acc[i] = 0.0;
-  for (int cb = 0; cb < C; cb += 128) {
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  for (int cb = 0; cb < C; cb += 64) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nb * 128; idx += blockDim.x) {
-      const int i = idx >> 7, k = idx & 127;
-      s_g[i][k] = (cb + k < C) ? gamma[(size_t)(b0 + i) * C + cb + k] : 0.0;
+    if (threadIdx.x < 64) s_any[threadIdx.x] = 0;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * IV_BCHUNK; idx += blockDim.x) {
+      const int k = idx / IV_BCHUNK, i = idx - k * IV_BCHUNK;
+      const double g = (i < nb && cb + k < C) ? gamma[(size_t)(b0 + i) * C + cb + k] : 0.0;
+      s_g[k][i] = g;
+      if (g != 0.0) s_any[k] = 1;
     }
     __syncthreads();
-    if (e < n_packed) {
-      const int kmax = min(128, C - cb);
-      for (int k = 0; k < kmax; ++k) {
-        const double u = (double)U[(size_t)(cb + k) * n_packed + e];
+    const int kmax = min(64, C - cb);
+    for (int k = 0; k < kmax; ++k) {
+      if (!s_any[k]) continue;
+      const float *row = U + (size_t)(cb + k) * n_packed + e0;
+      float p[4];
+      if (vec_ok) {
+        const float4 q = *reinterpret_cast<const float4 *>(row);
+        p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
+      } else {
 #pragma unroll
-        for (int i = 0; i < IV_BCHUNK; ++i) {
-          const double gk = s_g[i][k];
-          if (i < nb && gk != 0.0) acc[i] += gk * u;
-        }
+        for (int i = 0; i < 4; ++i) p[i] = (e0 + i < n_packed) ? row[i] : 0.f;
       }
+      const double2 *gr = reinterpret_cast<const double2 *>(&s_g[k][ug * 8]);
+      const double2 g01 = gr[0], g23 = gr[1], g45 = gr[2], g67 = gr[3];
+      const double gv[8] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y, g67.x, g67.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += (double)p[i] * gv[j];
     }
   }
-  if (e < n_packed)
 #pragma unroll
-    for (int i = 0; i < IV_BCHUNK; ++i)
-      if (i < nb) quad[(size_t)(b0 + i) * n_packed + e] = acc[i];
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = e0 + i, bi = ug * 8 + j;
+      if (e < n_packed && bi < nb) quad[(size_t)(b0 + bi) * n_packed + e] = acc[i][j];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per utterance: A = unpack(quad) + I, rhs = sum of lin partials (+ prior offset on element 0), Cholesky solve.
-// One CTA (512 threads) per utterance; A lives in global scratch [b][R][R] (L2 resident).
+// Per utterance: A = unpack(quad) + I, rhs = sum of lin partials (+ prior offset on element 0), blocked Cholesky
+// (panel width 32 in shared memory, rank-32 trailing updates), blocked forward / backward substitution.
+// One CTA (512 threads) per utterance; A lives in global scratch [b][R][R] (L2 resident), lower triangle only.
 // ------------------------------------------------------------------------------------------------
+#define IV_NB 32
+#define IV_PSTRIDE 33      // padded panel row stride (doubles): rows map to different banks
+
 __global__ void __launch_bounds__(512)
 ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ lin_part, int n_splits, int B, int R, int n_packed,
                   double prior_offset, double *__restrict__ Awork, float *__restrict__ ivec, int *__restrict__ err,
                   const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  extern __shared__ double s_v[];            // [R] rhs / solution, [R] column scratch
-  double *rhs = s_v, *colk = s_v + R;
+  extern __shared__ double s_dyn[];
+  double *rhs = s_dyn;                               // [R]
+  double *panel = s_dyn + R;                         // [R][IV_PSTRIDE]  rows k0..R-1 of the current block column
+  __shared__ double s_blk[IV_NB];
+  __shared__ int s_fail;
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   double *A = Awork + (size_t)b * R * R;
+  if (tid == 0) s_fail = 0;
   for (int idx = tid; idx < R * R; idx += nt) {
     const int i = idx / R, j = idx - i * R;
     if (j <= i) A[idx] = quad[(size_t)b * n_packed + (size_t)i * (i + 1) / 2 + j] + ((i == j) ? 1.0 : 0.0);
@@ -356,44 +409,146 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
     rhs[r] = acc + ((r == 0) ? prior_offset : 0.0);
   }
   __syncthreads();
-  // right-looking Cholesky on the lower triangle
-  for (int k = 0; k < R; ++k) {
-    const double akk = A[(size_t)k * R + k];
-    if (!(akk > 0.0)) { if (tid == 0) atomicExch(err, 3); return; }
-    const double d = sqrt(akk);
-    __syncthreads();
-    for (int i = k + tid; i < R; i += nt) {
-      const double v = (i == k) ? d : A[(size_t)i * R + k] / d;
-      A[(size_t)i * R + k] = v;
-      colk[i] = v;
+  for (int k0 = 0; k0 < R; k0 += IV_NB) {
+    const int nbk = min(IV_NB, R - k0);
+    const int rows = R - k0;                         // panel rows (global rows k0..R-1)
+    // load block column
+    for (int idx = tid; idx < rows * nbk; idx += nt) {
+      const int i = idx / nbk, j = idx - i * nbk;
+      panel[i * IV_PSTRIDE + j] = (k0 + j <= k0 + i) ? A[(size_t)(k0 + i) * R + k0 + j] : 0.0;
     }
     __syncthreads();
-    const int rem = R - k - 1;
-    // trailing update: rows i > k, columns k < j <= i ; warps take rows, lanes take columns (coalesced)
-    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-    for (int ii = warp; ii < rem; ii += nw) {
-      const int i = k + 1 + ii;
-      const double lik = colk[i];
-      for (int j = k + 1 + lane; j <= i; j += 32) A[(size_t)i * R + j] -= lik * colk[j];
+    // factor the diagonal block (warp 0), unblocked
+    if (warp == 0) {
+      for (int k = 0; k < nbk; ++k) {
+        const double akk = panel[k * IV_PSTRIDE + k];
+        if (!(akk > 0.0)) { if (lane == 0) s_fail = 1; break; }
+        const double d = sqrt(akk);
+        __syncwarp();
+        if (lane == k) panel[k * IV_PSTRIDE + k] = d;
+        if (lane > k && lane < nbk) panel[lane * IV_PSTRIDE + k] /= d;
+        __syncwarp();
+        // trailing update inside the block: element (i = lane, j) for k < j <= i
+        if (lane > k && lane < nbk) {
+          const double lik = panel[lane * IV_PSTRIDE + k];
+          for (int j = k + 1; j <= lane; ++j) panel[lane * IV_PSTRIDE + j] -= lik * panel[j * IV_PSTRIDE + k];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (s_fail) { if (tid == 0) atomicExch(err, 3); return; }
+    // rows below the diagonal block: L21 = A21 * L11^-T (one thread per row, forward substitution over the block)
+    for (int i = nbk + tid; i < rows; i += nt) {
+      double *row = panel + i * IV_PSTRIDE;
+      for (int j = 0; j < nbk; ++j) {
+        double v = row[j];
+        for (int q = 0; q < j; ++q) v -= row[q] * panel[j * IV_PSTRIDE + q];
+        row[j] = v / panel[j * IV_PSTRIDE + j];
+      }
+    }
+    __syncthreads();
+    // write the factored block column back
+    for (int idx = tid; idx < rows * nbk; idx += nt) {
+      const int i = idx / nbk, j = idx - i * nbk;
+      if (j <= i) A[(size_t)(k0 + i) * R + k0 + j] = panel[i * IV_PSTRIDE + j];
+    }
+    // trailing update A22 -= L21 L21^T on the lower triangle: 4x4 register tiles
+    const int rem = rows - nbk;                      // trailing dimension
+    const int nt4 = (rem + 3) / 4;
+    const int n_tiles = nt4 * (nt4 + 1) / 2;
+    for (int t = tid; t < n_tiles; t += nt) {
+      int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      while (ti * (ti + 1) / 2 > t) --ti;
+      const int tj = t - ti * (ti + 1) / 2;
+      const int i0 = nbk + ti * 4, j0 = nbk + tj * 4;       // panel-local row indices
+      double c[4][4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) c[x][y] = 0.0;
+      for (int q = 0; q < nbk; ++q) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          av[x] = (i0 + x < rows) ? panel[(i0 + x) * IV_PSTRIDE + q] : 0.0;
+          bv[x] = (j0 + x < rows) ? panel[(j0 + x) * IV_PSTRIDE + q] : 0.0;
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) c[x][y] += av[x] * bv[y];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const int gi = k0 + i0 + x, gj = k0 + j0 + y;
+          if (gi < R && gj <= gi && gj < R) A[(size_t)gi * R + gj] -= c[x][y];
+        }
     }
     __syncthreads();
   }
-  // forward substitution L y = rhs (column oriented), then backward L^T w = y
-  for (int k = 0; k < R; ++k) {
-    if (tid == 0) rhs[k] = rhs[k] / A[(size_t)k * R + k];
+  // forward substitution L y = rhs, blocked
+  for (int k0 = 0; k0 < R; k0 += IV_NB) {
+    const int nbk = min(IV_NB, R - k0);
+    if (warp == 0) {
+      double yv = (lane < nbk) ? rhs[k0 + lane] : 0.0;
+      double lrow[IV_NB];                              // row `lane` of the diagonal block
+#pragma unroll
+      for (int k = 0; k < IV_NB; ++k) lrow[k] = (lane < nbk && k <= lane) ? A[(size_t)(k0 + lane) * R + k0 + k] : 1.0;
+#pragma unroll
+      for (int k = 0; k < IV_NB; ++k) {
+        if (k < nbk) {
+          const double lkk = __shfl_sync(0xffffffffu, lrow[k], k);
+          const double yk = __shfl_sync(0xffffffffu, yv, k) / lkk;
+          if (lane == k) yv = yk;
+          if (lane > k && lane < nbk) yv -= lrow[k] * yk;
+        }
+      }
+      if (lane < nbk) { rhs[k0 + lane] = yv; s_blk[lane] = yv; }
+    }
     __syncthreads();
-    const double yk = rhs[k];
-    for (int i = k + 1 + tid; i < R; i += nt) rhs[i] -= A[(size_t)i * R + k] * yk;
+    for (int i = k0 + nbk + tid; i < R; i += nt) {
+      double v = rhs[i];
+      const double *row = A + (size_t)i * R + k0;
+      for (int j = 0; j < nbk; ++j) v -= row[j] * s_blk[j];
+      rhs[i] = v;
+    }
     __syncthreads();
   }
-  for (int k = R - 1; k >= 0; --k) {
-    if (tid == 0) rhs[k] = rhs[k] / A[(size_t)k * R + k];
+  // backward substitution L^T w = y, blocked from the last block
+  const int n_blocks = (R + IV_NB - 1) / IV_NB;
+  for (int bi = n_blocks - 1; bi >= 0; --bi) {
+    const int k0 = bi * IV_NB;
+    const int nbk = min(IV_NB, R - k0);
+    if (warp == 0) {
+      double wv = (lane < nbk) ? rhs[k0 + lane] : 0.0;
+      double lcol[IV_NB];                              // column `lane` of the diagonal block
+#pragma unroll
+      for (int k = 0; k < IV_NB; ++k) lcol[k] = (k < nbk && lane <= k) ? A[(size_t)(k0 + k) * R + k0 + lane] : 1.0;
+#pragma unroll
+      for (int k = IV_NB - 1; k >= 0; --k) {
+        if (k < nbk) {
+          const double lkk = __shfl_sync(0xffffffffu, lcol[k], k);
+          const double wk = __shfl_sync(0xffffffffu, wv, k) / lkk;
+          if (lane == k) wv = wk;
+          if (lane < k) wv -= lcol[k] * wk;
+        }
+      }
+      if (lane < nbk) { rhs[k0 + lane] = wv; s_blk[lane] = wv; }
+    }
     __syncthreads();
-    const double wk = rhs[k];
-    for (int i = tid; i < k; i += nt) rhs[i] -= A[(size_t)k * R + i] * wk;
+    for (int i = tid; i < k0; i += nt) {
+      double v = rhs[i];
+      for (int j = 0; j < nbk; ++j) v -= A[(size_t)(k0 + j) * R + i] * s_blk[j];
+      rhs[i] = v;
+    }
     __syncthreads();
   }
   for (int r = tid; r < R; r += nt) ivec[(size_t)b * R + r] = (float)(rhs[r] - ((r == 0) ? prior_offset : 0.0));
+  (void)nw;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -716,9 +871,11 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   const int rows = ctx->total_frames;           // upper bound of the voiced rows (device knows the exact count)
   if ((rc = fb_run_gmm_store(ctx, v->ll.p, done_flag))) return rc;
   gselect_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(v->ll.p, ctx->misc.p, v->C, v->gsel.p, done_flag);
+  fb_prof_mark(ctx, 8);
   fgmm_post_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->gconsts.p, v->means_invcovars.p,
                                                                   v->inv_covars.p, v->rc_table.p, ctx->misc.p, v->min_post, v->post.p,
                                                                   done_flag);
+  fb_prof_mark(ctx, 9);
   const int max_pairs = ctx->max_frames * IV_NSEL;
   const size_t smem_stats = (size_t)(3 * v->C + 1) * sizeof(int) + (size_t)(2 * max_pairs + 2) * sizeof(unsigned short) +
                             (size_t)2 * max_pairs * sizeof(float) + 16;
@@ -734,15 +891,25 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   }
   ivec_stats_kernel<<<B, 256, smem_stats, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->post.p, ctx->row_off.p, v->C, max_pairs,
                                                          v->gamma.p, v->Xs.p, ctx->misc.p + 1, done_flag);
+  fb_prof_mark(ctx, 10);
   const int bch = fb_div_up(B, IV_BCHUNK);
-  const int lin_threads = ((v->R + 31) / 32) * 32;
+  const int lin_threads = ((4 * ((v->R + 3) / 4) + 31) / 32) * 32;
   ivec_lin_kernel<<<dim3(v->n_splits, bch), lin_threads, 0, ctx->stream>>>(v->sim32.p, v->Xs.p, v->gamma.p, B, v->C, v->R,
                                                                           v->n_splits, v->lin_part.p, done_flag);
+  fb_prof_mark(ctx, 11);
   ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, B, v->C, v->n_packed,
                                                                                    v->quad.p, done_flag);
-  ivec_solve_kernel<<<B, 512, 2 * v->R * sizeof(double), ctx->stream>>>(v->quad.p, v->lin_part.p, v->n_splits, B, v->R, v->n_packed,
+  fb_prof_mark(ctx, 12);
+  const size_t smem_solve = ((size_t)v->R + (size_t)v->R * IV_PSTRIDE) * sizeof(double);
+  static bool attr_solve = false;
+  if (!attr_solve) {
+    FB_CUDA(cudaFuncSetAttribute(ivec_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_solve = true;
+  }
+  ivec_solve_kernel<<<B, 512, smem_solve, ctx->stream>>>(v->quad.p, v->lin_part.p, v->n_splits, B, v->R, v->n_packed,
                                                                         v->prior_offset, v->Awork.p, v->ivec.p, ctx->misc.p + 1,
                                                                         done_flag);
+  fb_prof_mark(ctx, 13);
   ctx->launches += 6;
   if (with_plda) {
     const size_t smem_plda = (size_t)v->L * sizeof(double) + (size_t)(v->R + v->L) * sizeof(float) + 16;
@@ -750,7 +917,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
                                                     v->psi.p, v->u_train.p, v->R, v->L, v->K, v->scores.p, done_flag);
     ctx->launches += 1;
   }
-  fb_prof_mark(ctx, 5);
+  fb_prof_mark(ctx, 14);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }

@@ -222,15 +222,16 @@ class GmmEngine:
         _lib.check(self.lib.fb_nes_kernel_launches(self.h, C.byref(n)))
         return n.value
 
-    STAGES = ("perturb", "mfcc", "vad_scan", "feats", "gmm", "gmm_reduce", "loss", "update")
+    STAGES = ("perturb", "mfcc", "vad_scan", "feats", "gmm", "gmm_reduce", "loss", "update",
+              "gselect", "fgmm_post", "ivec_stats", "ivec_lin", "ivec_quad", "ivec_solve", "plda", "spare")
 
     def profile(self, on=True):
         _lib.check(self.lib.fb_profile_enable(self.h, 1 if on else 0))
 
     def profile_read(self):
         """-> {stage: (total_ms, launches)} accumulated since profile(True)."""
-        ms = np.zeros(8, dtype=np.float64)
-        cnt = np.zeros(8, dtype=np.int64)
+        ms = np.zeros(16, dtype=np.float64)
+        cnt = np.zeros(16, dtype=np.int64)
         _lib.check(self.lib.fb_profile_read(self.h, _ptr(ms), _ptr(cnt)))
         return {s: (float(ms[i]), int(cnt[i])) for i, s in enumerate(self.STAGES)}
 

@@ -155,9 +155,10 @@ int fb_nes_apply_update(fb_ctx *ctx, double lr);
 int fb_nes_kernel_launches(fb_ctx *ctx, int64_t *count);
 
 /* ---- per-stage device timing (CUDA events on the context's stream; disables graph replay while on) ----
- * Stage ids: 0 perturb, 1 mfcc, 2 vad_scan, 3 feats, 4 gmm, 5 gmm_reduce, 6 loss, 7 update(+collective).
+ * Stage ids: 0 perturb, 1 mfcc, 2 vad_scan, 3 feats, 4 gmm, 5 gmm_reduce, 6 loss, 7 update(+collective),
+ * 8 gselect, 9 fgmm_post, 10 ivec_stats, 11 ivec_lin, 12 ivec_quad, 13 ivec_solve, 14 plda.
  * fb_profile_read returns accumulated milliseconds and launch counts per stage since fb_profile_enable(ctx, 1). */
-#define FB_PROF_STAGES 8
+#define FB_PROF_STAGES 16
 int fb_profile_enable(fb_ctx *ctx, int on);
 int fb_profile_read(fb_ctx *ctx, double *ms_host, int64_t *count_host);
 /* Total voiced rows (frames) of the last scored batch: the GMM kernel's M dimension. */
