@@ -15,9 +15,13 @@
 #define FB_NCEPS       24
 #define FB_DIM         72      // 24 x (static, delta, delta-delta)
 #define FB_KSLABS      18      // K = 144 = [x | x^2] in slabs of 8 fp16
-#define FB_A_HI_SLABS  20      // + the "ones" slab (gconst rides in the MMA) + one zero slab
-#define FB_A_TILE_SLABS 38     // hi 20 + lo 18 slabs per 128-row tile
-#define FB_W_HI_SLABS  20      // + gconst slab + zero slab
+// Operand K layout (slabs of 8 fp16), identical for the hi and the lo half of A and W:
+//   [x: 0..8] [ones / gconst: 9] [x^2: 10..18] [zero: 19]      -> the x half and the x^2 half are 5 k-blocks (K=80) each
+#define FB_A_HI_SLABS  20
+#define FB_A_TILE_SLABS 40     // hi 20 + lo 20 slabs per 128-row tile
+#define FB_W_HI_SLABS  20
+#define FB_SLAB_ONES   9
+#define FB_SLAB_X2     10
 #define FB_TILE_M      128
 #define FB_STAGE_N     64      // W columns per smem stage
 #define FB_CHUNK_N     128     // accumulator columns per (tile, unit)
@@ -108,7 +112,8 @@ struct fb_ctx {
   FbHostGmm host_gmm[FB_MAX_MODELS];
   int n_models = 0, C = 0;
   int gmm_impl = 0;
-  DevBuf<__half> w_img;        // [model][C/64][2][18][64][8]
+  DevBuf<__half> w_img;        // general: [model][C/64][hi 20 | lo 20 slabs][64][8]; shared-variance: [C/64][1+models][hi 10 | lo 10][64][8]
+  bool gmm_shared = false;     // all models share inv_vars (MAP mean-only adaptation): x^2 contraction done once
   DevBuf<float>  gconst2;      // [model][C]  gconst * log2(e)
   DevBuf<float>  w_f32;        // [model][C][144] (means_invvars | -0.5 inv_vars), cross-check kernel
   DevBuf<float>  gconst_nat;   // [model][C]

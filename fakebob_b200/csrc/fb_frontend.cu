@@ -344,7 +344,7 @@ vad_scan_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_of
 // ------------------------------------------------------------------------------------------------
 // Deltas (order 2, window 3), sliding CMN (centred window, float64 prefix sums), voiced-row compaction,
 // per-dimension power-of-two scaling and the fp16 hi/lo split of [x | x^2], written straight into the
-// tensor-core operand image  a_img[tile][hi: 19 slabs | lo: 18 slabs][row 128][8 halfs].
+// tensor-core operand image  a_img[tile][hi: 20 slabs | lo: 20 slabs][row 128][8 halfs]  (slab order: x, ones, x^2, zero).
 // One CTA per (utterance, output slab): slab sl = 3*order + cepstra-group holds dims d = 24*order + 8*cg + 0..7,
 // so each CTA owns x-slab sl and x^2-slab 9+sl and every store is a full 16-byte row chunk.
 // ------------------------------------------------------------------------------------------------
@@ -457,17 +457,17 @@ feats_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_off, 
     *reinterpret_cast<uint4 *>(tbase + (size_t)sl * (FB_TILE_M * 8)) = hi;
     *reinterpret_cast<uint4 *>(tbase + (size_t)(FB_A_HI_SLABS + sl) * (FB_TILE_M * 8)) = lo;
     split_pack8(x2, hi, lo);
-    *reinterpret_cast<uint4 *>(tbase + (size_t)(9 + sl) * (FB_TILE_M * 8)) = hi;
-    *reinterpret_cast<uint4 *>(tbase + (size_t)(FB_A_HI_SLABS + 9 + sl) * (FB_TILE_M * 8)) = lo;
+    *reinterpret_cast<uint4 *>(tbase + (size_t)(FB_SLAB_X2 + sl) * (FB_TILE_M * 8)) = hi;
+    *reinterpret_cast<uint4 *>(tbase + (size_t)(FB_A_HI_SLABS + FB_SLAB_X2 + sl) * (FB_TILE_M * 8)) = lo;
   }
 }
 
-// The "ones" slab (hi slab 18) of every tile: columns 0..2 = 1.0 so the three fp16 terms of gconst in W add up in the MMA.
+// The "ones" slab (hi slab 9) of every tile: columns 0..2 = 1.0 so the three fp16 terms of gconst in W add up in the MMA.
 __global__ void a_img_init_kernel(__half *a_img, int n_tiles) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_tiles * FB_TILE_M) return;
   const int tile = idx / FB_TILE_M, rr = idx - tile * FB_TILE_M;
-  __half *p = a_img + ((size_t)tile * FB_A_TILE_SLABS + FB_KSLABS) * (FB_TILE_M * 8) + rr * 8;
+  __half *p = a_img + ((size_t)tile * FB_A_TILE_SLABS + FB_SLAB_ONES) * (FB_TILE_M * 8) + rr * 8;
   const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
   p[0] = one; p[1] = one; p[2] = one;
 #pragma unroll

@@ -32,28 +32,33 @@
 #define GMM_PARTS 3
 #endif
 #define GMM_THREADS 320                       // producer warp + MMA warp + 8 epilogue warps
-// A image per 128-row tile: hi = 20 slabs (9 x, 9 x^2, 1 "ones" slab carrying the gconst columns, 1 zero slab), lo = 18 slabs.
-// W image per 64-column stage: hi = 20 slabs (18 + gconst slab [g_hi g_mid g_lo 0..] + zero slab), lo = 18 slabs.
+// Operand K layout (slabs of 8 fp16) for the hi and lo halves of A and W alike:
+//   [x 0..8][ones | gconst 9][x^2 10..18][zero 19]   (20 slabs = 10 k-blocks of K=16; each half is 5 k-blocks)
+// gconst*log2(e) sits in W's slab 9 as three fp16 terms (g_hi, g_mid, g_lo) against three 1.0 columns of A's "ones" slab,
+// so it is added inside the MMA and the epilogue never touches it.
 static constexpr uint32_t kSlabA = FB_TILE_M * 16;                             // 2048 B
 static constexpr uint32_t kSlabW = FB_STAGE_N * 16;                            // 1024 B
-static constexpr uint32_t kAHiBytes = FB_A_HI_SLABS * kSlabA;                  // 40960
-static constexpr uint32_t kALoBytes = FB_KSLABS * kSlabA;                      // 36864
-static constexpr uint32_t kATileBytes = kAHiBytes + kALoBytes;                 // 77824
-static constexpr uint32_t kWHiBytes = FB_W_HI_SLABS * kSlabW;                  // 20480
-static constexpr uint32_t kWLoBytes = FB_KSLABS * kSlabW;                      // 18432
-static constexpr uint32_t kWStageBytes = kWHiBytes + kWLoBytes;                // 38912
+static constexpr uint32_t kAHalfBytes = FB_A_HI_SLABS * kSlabA;                // 40960 (hi or lo of one tile)
+static constexpr uint32_t kATileBytes = 2 * kAHalfBytes;                       // 81920
+static constexpr uint32_t kWHalfBytes = FB_W_HI_SLABS * kSlabW;                // 20480 (hi or lo of one general stage)
+static constexpr uint32_t kWStageBytes = 2 * kWHalfBytes;                      // 40960
+static constexpr uint32_t kWShHalfBytes = 10 * kSlabW;                         // 10240 (hi or lo of one shared-mode sub-stage)
+static constexpr uint32_t kWShBytes = 2 * kWShHalfBytes;                       // 20480
 static constexpr uint32_t kSlotBytes = 40960;
 static constexpr uint32_t kNumSlots = 5;
 static constexpr uint32_t kSmemBar = kNumSlots * kSlotBytes;                   // 204800
 static constexpr uint32_t kSmemTotal = kSmemBar + 256;
 static constexpr uint32_t kSmemLaunch = kSmemTotal + 128;                      // 128 B alignment slack
-static_assert(kAHiBytes <= kSlotBytes && kWStageBytes <= kSlotBytes, "ring slot too small");
+static_assert(kAHalfBytes <= kSlotBytes && kWStageBytes <= kSlotBytes, "ring slot too small");
 static_assert(kSmemLaunch <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-// TMEM columns: accumulators [0,128) (tile0 | tile1, 64 each); A operand: tile t hi at 128 + 152 t, lo 80 columns later
+// TMEM columns (all 512 used): three 64-column accumulators [0,192) used as a ring over (tile, sub-step) jobs, so the
+// MMA <-> epilogue hand-shake latency is hidden behind two jobs; A operand: tile t at 192 + 160 t: hi 80 columns, lo 80 columns
 static constexpr uint32_t kTmemAcc = 0;
-static constexpr uint32_t kTmemA = 128;
-static constexpr uint32_t kTmemAHiCols = FB_A_HI_SLABS * 4;                    // 80
-static constexpr uint32_t kTmemATileCols = kTmemAHiCols + FB_KSLABS * 4;       // 152
+static constexpr uint32_t kNumAcc = 3;
+static constexpr uint32_t kTmemA = 192;
+static constexpr uint32_t kTmemAHalfCols = FB_A_HI_SLABS * 4;                  // 80
+static constexpr uint32_t kTmemATileCols = 2 * kTmemAHalfCols;                 // 160
+static constexpr uint32_t kTmemX2Cols = FB_SLAB_X2 * 4;                        // 40: column offset of the x^2 half
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -167,33 +172,45 @@ struct GmmArgs {
   int n_models, C, rows_cap;
 };
 
-// One 32-column group of one accumulator row: online max / sum of 2^(v - max) with Kaldi's cutoff.
+// One 32-column batch of one accumulator row: online max / sum of 2^(v - max) with Kaldi's cutoff (LogSumExp drops terms
+// below max + log(FLT_EPSILON) = max - 23 in log2).  Only ~0.5 % of the terms survive that cutoff, so the exponentials are
+// evaluated per 8-column group and only when a warp vote finds a lane that still needs them (measured on the C2 model:
+// ~75 % of the warp x 8-column groups are dead).  `m` is the running row maximum, `s` the sum relative to it.
 __device__ __forceinline__ void lse_group(const float *v, float &m, float &s) {
-  float c0 = max3(v[0], v[1], v[2]), c1 = max3(v[3], v[4], v[5]);
+  float gmax[4];
 #pragma unroll
-  for (int i = 6; i < 30; i += 6) {
-    c0 = max3(c0, v[i], v[i + 1]);
-    c0 = fmaxf(c0, v[i + 2]);
-    c1 = max3(c1, v[i + 3], v[i + 4]);
-    c1 = fmaxf(c1, v[i + 5]);
+  for (int k = 0; k < 4; ++k) {
+    const float *q = v + 8 * k;
+    gmax[k] = max3(max3(q[0], q[1], q[2]), max3(q[3], q[4], q[5]), fmaxf(q[6], q[7]));
   }
-  const float cmax = max3(c0, c1, fmaxf(v[30], v[31]));
+  const float cmax = max3(gmax[0], gmax[1], fmaxf(gmax[2], gmax[3]));
   if (cmax > m) {
     s *= ex2_approx(m - cmax);
     m = cmax;
   }
-  float s0 = 0.f, s1 = 0.f;
+  const float thr = m - 23.0f;
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    const float t0 = v[i] - m, t1 = v[i + 1] - m;
-    const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
-    if (t0 >= -23.0f) s0 += e0;                 // Kaldi LogSumExp cutoff log(FLT_EPSILON) = -23 in log2
-    if (t1 >= -23.0f) s1 += e1;
+  for (int k = 0; k < 4; ++k) {
+    if (__any_sync(0xffffffffu, gmax[k] >= thr)) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const float t0 = v[8 * k + i] - m, t1 = v[8 * k + i + 1] - m;
+        const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+        if (t0 >= -23.0f) s0 += e0;
+        if (t1 >= -23.0f) s1 += e1;
+      }
+      s += s0 + s1;
+    }
   }
-  s += s0 + s1;
 }
 
-template <bool kStore>
+// kShared: all models share the inverse variances (MAP mean-only adaptation, build_spk_models.py:170), so per
+// (super-tile, 64-column stage) the x^2 contraction  Q = x^2 . (-0.5/var)  is computed ONCE, read by the epilogue into
+// registers, and every model only needs  T_m = x . (mu_m/var) + g_m  (15 MMAs instead of 30); the epilogue forms
+// ll_m = Q + T_m.  Every accumulator starts from zero, so the (truncating) tensor-core accumulation error is the same for
+// all models and cancels in log-likelihood-ratio scores.
+template <bool kStore, bool kShared>
 __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   if (g.done_flag && *g.done_flag) return;
   extern __shared__ uint8_t smem_raw[];
@@ -202,25 +219,28 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   uint8_t *smem = smem_raw + (base - raw_addr);
   const uint32_t bar0 = base + kSmemBar;
   const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kNumSlots;           // ring slots
-  const uint32_t bar_acc_full = bar0 + 16 * kNumSlots, bar_acc_empty = bar_acc_full + 16;   // [2 tiles] each
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmemBar + 16 * kNumSlots + 32);
+  const uint32_t bar_acc_full = bar0 + 16 * kNumSlots, bar_acc_empty = bar_acc_full + 8 * kNumAcc;   // [kNumAcc] each
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmemBar + 16 * kNumSlots + 16 * kNumAcc + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.misc[2];
   const int nch = g.C / FB_CHUNK_N;
   const int n_super = (M + 2 * FB_TILE_M - 1) / (2 * FB_TILE_M);
-  const long long n_units = (long long)n_super * g.n_models * nch;
+  // general: unit = (super, model, chunk); shared: unit = (super, chunk), all models inside
+  const int models_per_unit = kShared ? 1 : g.n_models;
+  const long long n_units = (long long)n_super * models_per_unit * nch;
   const int u0 = (int)(n_units * blockIdx.x / gridDim.x);
   const int u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
+  const int n_sub = kShared ? g.n_models + 1 : 1;                              // ring entries per 64-column stage
 
   if (warp == 0 && lane == 0) {
     for (uint32_t i = 0; i < kNumSlots; ++i) {
       mbar_init(bar_full + 8 * i, 1);
       mbar_init(bar_empty + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (uint32_t i = 0; i < kNumAcc; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 4);     // one arrive per epilogue warp of that tile
+      mbar_init(bar_acc_empty + 8 * i, 4);     // one arrive per epilogue warp of the tile that read it
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,8 +261,8 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     for (int u = u0; u < u1; ++u) {
       const int ch = u % nch;
       const int item = u / nch;
-      const int model = item % g.n_models;
-      const int sp = item / g.n_models;
+      const int model = item % models_per_unit;
+      const int sp = item / models_per_unit;
       if (sp != cur_super) {
         const uint8_t *src = reinterpret_cast<const uint8_t *>(g.a_img) + (size_t)sp * 2 * kATileBytes;
 #pragma unroll 1
@@ -250,10 +270,8 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           const uint32_t slot = cnt % kNumSlots;
           mbar_wait(bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
           if (elect_one()) {
-            const uint32_t bytes = (e & 1) ? kALoBytes : kAHiBytes;
-            mbar_expect_tx(bar_full + 8 * slot, bytes);
-            bulk_g2s(base + slot * kSlotBytes, src + (size_t)(e >> 1) * kATileBytes + ((e & 1) ? kAHiBytes : 0), bytes,
-                     bar_full + 8 * slot);
+            mbar_expect_tx(bar_full + 8 * slot, kAHalfBytes);
+            bulk_g2s(base + slot * kSlotBytes, src + (size_t)e * kAHalfBytes, kAHalfBytes, bar_full + 8 * slot);
           }
           __syncwarp();
           ++cnt;
@@ -262,16 +280,20 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       }
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        const uint32_t slot = cnt % kNumSlots;
-        mbar_wait(bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(bar_full + 8 * slot, kWStageBytes);
-          const size_t stage_idx = (size_t)model * (g.C / FB_STAGE_N) + (size_t)ch * 2 + h;
-          bulk_g2s(base + slot * kSlotBytes, reinterpret_cast<const uint8_t *>(g.w_img) + stage_idx * kWStageBytes,
-                   kWStageBytes, bar_full + 8 * slot);
+        const size_t stage = (size_t)ch * 2 + h;
+#pragma unroll 1
+        for (int q = 0; q < n_sub; ++q) {
+          const uint32_t slot = cnt % kNumSlots;
+          mbar_wait(bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+          if (elect_one()) {
+            const uint32_t bytes = kShared ? kWShBytes : kWStageBytes;
+            const size_t idx = kShared ? (stage * n_sub + q) : ((size_t)model * (g.C / FB_STAGE_N) + stage);
+            mbar_expect_tx(bar_full + 8 * slot, bytes);
+            bulk_g2s(base + slot * kSlotBytes, reinterpret_cast<const uint8_t *>(g.w_img) + idx * bytes, bytes, bar_full + 8 * slot);
+          }
+          __syncwarp();
+          ++cnt;
         }
-        __syncwarp();
-        ++cnt;
       }
     }
   } else if (warp == 1) {
@@ -280,10 +302,10 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     const uint64_t desc_w = make_desc(0, kSlabW, 128);
     const uint64_t desc_a = make_desc(0, kSlabA, 128);
     int cur_super = -1;
-    uint32_t cnt = 0, sub0 = 0, sub1 = 0;
+    uint32_t cnt = 0, job = 0;                      // job = running (tile, sub-step) counter; accumulator = job % 3
     for (int u = u0; u < u1; ++u) {
       const int item = u / nch;
-      const int sp = item / g.n_models;
+      const int sp = item / models_per_unit;
       if (sp != cur_super) {
 #pragma unroll 1
         for (int e = 0; e < 4; ++e) {
@@ -292,9 +314,9 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           tc_fence_after();
           if (elect_one()) {
             const uint64_t src = desc_a + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
-            const uint32_t dst = tmem_base + kTmemA + (e >> 1) * kTmemATileCols + ((e & 1) ? kTmemAHiCols : 0);
-            const int nkb = (e & 1) ? FB_KSLABS / 2 : FB_A_HI_SLABS / 2;
-            for (int kb = 0; kb < nkb; ++kb) tc_cp_128x256b(dst + kb * 8, src + (uint64_t)(kb * ((2 * kSlabA) >> 4)));
+            const uint32_t dst = tmem_base + kTmemA + (e >> 1) * kTmemATileCols + (e & 1) * kTmemAHalfCols;
+#pragma unroll
+            for (int kb = 0; kb < FB_A_HI_SLABS / 2; ++kb) tc_cp_128x256b(dst + kb * 8, src + (uint64_t)(kb * ((2 * kSlabA) >> 4)));
             tc_commit(bar_empty + 8 * slot);
           }
           __syncwarp();
@@ -304,76 +326,114 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       }
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        const uint32_t slot = cnt % kNumSlots;
-        mbar_wait(bar_full + 8 * slot, (cnt / kNumSlots) & 1);
-        const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
-        const uint64_t w_lo = w_hi + (uint64_t)(kWHiBytes >> 4);
+#pragma unroll 1
+        for (int q = 0; q < n_sub; ++q) {
+          const uint32_t slot = cnt % kNumSlots;
+          mbar_wait(bar_full + 8 * slot, (cnt / kNumSlots) & 1);
+          const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
+          const uint64_t w_lo = w_hi + (uint64_t)((kShared ? kWShHalfBytes : kWHalfBytes) >> 4);
+          // shared mode: q = 0 is the x^2 sub-step, q >= 1 the x (+ gconst) sub-step of model q-1; all start from zero
+          const uint32_t a_off = (kShared && q == 0) ? kTmemX2Cols : 0;
 #pragma unroll
-        for (int tile = 0; tile < 2; ++tile) {
-          mbar_wait(bar_acc_empty + 8 * tile, ((tile ? sub1 : sub0) & 1) ^ 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols;
-            const uint32_t a_lo = a_hi + kTmemAHiCols;
-            const uint32_t d_tmem = tmem_base + kTmemAcc + tile * FB_STAGE_N;
+          for (int tile = 0; tile < 2; ++tile) {
+            const uint32_t abuf = job % kNumAcc;
+            mbar_wait(bar_acc_empty + 8 * abuf, ((job / kNumAcc) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols + a_off;
+              const uint32_t a_lo = a_hi + kTmemAHalfCols;
+              const uint32_t d_tmem = tmem_base + kTmemAcc + abuf * FB_STAGE_N;
+              constexpr int nkb = kShared ? 5 : 10;
 #pragma unroll
-            for (int part = 0; part < GMM_PARTS; ++part) {
-              const uint32_t a_base = (part == 1) ? a_lo : a_hi;
-              const uint64_t b_base = (part == 2) ? w_lo : w_hi;
-              const int nkb = (part == 0) ? FB_A_HI_SLABS / 2 : FB_KSLABS / 2;      // part 0 carries the gconst k-block
+              for (int part = 0; part < GMM_PARTS; ++part) {
+                const uint32_t a_base = (part == 1) ? a_lo : a_hi;
+                const uint64_t b_base = (part == 2) ? w_lo : w_hi;
 #pragma unroll
-              for (int kb = 0; kb < nkb; ++kb)
-                tc_mma_f16_ta(d_tmem, a_base + kb * 8, b_base + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
+                for (int kb = 0; kb < nkb; ++kb) {
+                  tc_mma_f16_ta(d_tmem, a_base + kb * 8, b_base + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
+                }
+              }
+              tc_commit(bar_acc_full + 8 * abuf);
+              if (tile == 1) tc_commit(bar_empty + 8 * slot);
             }
-            tc_commit(bar_acc_full + 8 * tile);
-            if (tile == 1) tc_commit(bar_empty + 8 * slot);
+            __syncwarp();
+            ++job;
           }
-          __syncwarp();
-          if (tile) ++sub1; else ++sub0;
+          ++cnt;
         }
-        ++cnt;
       }
     }
   } else {
     // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, tile = (warp - 2) / 4 =====
     const int quad = warp & 3;
     const int tile = (warp - 2) >> 2;
-    uint32_t sub = 0;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc + tile * FB_STAGE_N;
+    uint32_t job = tile;                               // this tile's jobs are tile, tile + 2, tile + 4, ...
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc;
+    const int n_read = kShared ? g.n_models + 1 : 1;   // accumulator reads per 64-column stage (shared: Q, then each model)
+    float mm[kShared ? FB_MAX_MODELS + 1 : 1], ss[kShared ? FB_MAX_MODELS + 1 : 1];
+    int run_item = -1;                                  // the running maxima belong to this (super[, model])
     for (int u = u0; u < u1; ++u) {
       const int ch = u % nch;
       const int item = u / nch;
-      const int model = item % g.n_models;
-      const int sp = item / g.n_models;
-      float m = -INFINITY, s = 0.f;
+      const int model = item % models_per_unit;
+      const int sp = item / models_per_unit;
+      const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
+      // the running row maximum is kept across consecutive 128-column units of the same rows and model, so the cutoff is
+      // (almost) relative to the global maximum; each unit still writes its own (max, sum) partial
+      for (int i = 0; i < n_read; ++i) {
+        if (item != run_item) mm[i] = -INFINITY;
+        ss[i] = 0.f;
+      }
+      run_item = item;
+      float qa[kShared ? 32 : 1], qb[kShared ? 32 : 1];   // shared mode: the x^2 term of this stage
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        mbar_wait(bar_acc_full + 8 * tile, sub & 1);
-        tc_fence_after();
-        float va[32], vb[32];
-        tc_ld32(taddr, va);
-        tc_ld32(taddr + 32, vb);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * tile);     // accumulator is in registers: MMA may overwrite
-        ++sub;
-        if (kStore) {
-          const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
-          float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + ch * FB_CHUNK_N + h * FB_STAGE_N);
-          const float ln2 = 0.6931471805599453f;
+#pragma unroll 1
+        for (int r = 0; r < n_read; ++r) {
+          const uint32_t abuf = job % kNumAcc;
+          mbar_wait(bar_acc_full + 8 * abuf, (job / kNumAcc) & 1);
+          tc_fence_after();
+          float va[32], vb[32];
+          const uint32_t taddr = taddr0 + abuf * FB_STAGE_N;
+          tc_ld32(taddr, va);
+          tc_ld32(taddr + 32, vb);
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * abuf);     // accumulator is in registers: MMA may overwrite
+          job += 2;
+          if (kStore) {
+            float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + ch * FB_CHUNK_N + h * FB_STAGE_N);
+            const float ln2 = 0.6931471805599453f;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(va[i] * ln2, va[i + 1] * ln2, va[i + 2] * ln2, va[i + 3] * ln2);
+            for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(va[i] * ln2, va[i + 1] * ln2, va[i + 2] * ln2, va[i + 3] * ln2);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) dst[8 + (i >> 2)] = make_float4(vb[i] * ln2, vb[i + 1] * ln2, vb[i + 2] * ln2, vb[i + 3] * ln2);
-        } else {
-          lse_group(va, m, s);
-          lse_group(vb, m, s);
+            for (int i = 0; i < 32; i += 4) dst[8 + (i >> 2)] = make_float4(vb[i] * ln2, vb[i + 1] * ln2, vb[i + 2] * ln2, vb[i + 3] * ln2);
+          } else if (kShared && r == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { qa[i] = va[i]; qb[i] = vb[i]; }
+          } else {
+            if (kShared) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { va[i] += qa[i]; vb[i] += qb[i]; }
+            }
+            float m = mm[r], sacc = ss[r];
+#ifndef GMM_NO_LSE
+            lse_group(va, m, sacc);
+            lse_group(vb, m, sacc);
+#else
+            m = fmaxf(m, va[0] + vb[31]);
+#endif
+            mm[r] = m;
+            ss[r] = sacc;
+          }
         }
       }
       if (!kStore) {
-        const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
-        g.part[((size_t)model * nch + ch) * g.rows_cap + row] = make_float2(m, s);
+        for (int r = kShared ? 1 : 0; r < n_read; ++r) {
+          const int mdl = kShared ? r - 1 : model;
+          g.part[((size_t)mdl * nch + ch) * g.rows_cap + row] = make_float2(mm[r], ss[r]);
+        }
       }
     }
   }
@@ -404,7 +464,8 @@ gmm_simt_kernel(const __half *__restrict__ a_img, const float *__restrict__ w_f3
   for (int idx = threadIdx.x; idx < 32 * 2 * FB_DIM; idx += blockDim.x) {
     const int r = idx / (2 * FB_DIM), k = idx % (2 * FB_DIM);
     const int row = row0 + r;
-    const int tile = row >> 7, rr = row & 127, slab = k >> 3, e = k & 7;
+    const int tile = row >> 7, rr = row & 127, e = k & 7;
+    const int slab = (k < FB_DIM) ? (k >> 3) : (FB_SLAB_X2 + ((k - FB_DIM) >> 3));
     const size_t b = ((size_t)tile * FB_A_TILE_SLABS + slab) * (FB_TILE_M * 8) + rr * 8 + e;
     float v = __half2float(a_img[b]) + __half2float(a_img[b + (size_t)FB_A_HI_SLABS * FB_TILE_M * 8]);
     const int d = (k < FB_DIM) ? k : k - FB_DIM;
@@ -436,30 +497,41 @@ gmm_simt_kernel(const __half *__restrict__ a_img, const float *__restrict__ w_f3
 }
 
 // ------------------------------------------------------------------------------------------------
-// Merge the per-chunk partials into per-frame log-likelihoods and the per-utterance average
-// (gmm-global-get-frame-likes --average=true: float frame values, double sum, float quotient).
-// grid (B, n_models), block 128, fixed reduction order (deterministic).
+// Merge the per-chunk partials into per-frame log-likelihoods (one thread per (row, model)), then the per-utterance
+// average (gmm-global-get-frame-likes --average=true: float frame values, double sum, float quotient).
+// Fixed reduction order (deterministic).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-gmm_reduce_kernel(const float2 *__restrict__ part, const int *__restrict__ row_off, float *__restrict__ frame_ll,
-                  double *__restrict__ avg_ll, int n_models, int nch, int rows_cap, const int *__restrict__ done_flag) {
+gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, float *__restrict__ frame_ll, int nch,
+                 int rows_cap, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int model = blockIdx.y;
+  if (row >= misc[2]) return;
+  float2 p[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < nch) {
+      p[k] = part[((size_t)model * nch + k) * rows_cap + row];
+      mx = fmaxf(mx, p[k].x);
+    }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < nch && p[k].x >= mx - 23.0f) s += (double)(p[k].y * exp2f(p[k].x - mx));
+  frame_ll[(size_t)model * rows_cap + row] = (float)(((double)mx + log2(s)) * 0.6931471805599453);
+}
+
+__global__ void __launch_bounds__(128)
+gmm_reduce_kernel(const float *__restrict__ frame_ll, const int *__restrict__ row_off, double *__restrict__ avg_ll,
+                  int n_models, int rows_cap, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
   __shared__ double s_red[4];
   const int b = blockIdx.x, model = blockIdx.y;
   const int r0 = row_off[b], r1 = row_off[b + 1];
   double acc = 0.0;
-  for (int row = r0 + threadIdx.x; row < r1; row += blockDim.x) {
-    float mx = -INFINITY;
-    for (int k = 0; k < nch; ++k) mx = fmaxf(mx, part[((size_t)model * nch + k) * rows_cap + row].x);
-    double s = 0.0;
-    for (int k = 0; k < nch; ++k) {
-      const float2 p = part[((size_t)model * nch + k) * rows_cap + row];
-      if (p.x >= mx - 23.0f) s += (double)p.y * exp2((double)(p.x - mx));
-    }
-    const float ll = (float)(((double)mx + log2(s)) * 0.6931471805599453);
-    frame_ll[(size_t)model * rows_cap + row] = ll;
-    acc += (double)ll;
-  }
+  for (int row = r0 + threadIdx.x; row < r1; row += blockDim.x) acc += (double)frame_ll[(size_t)model * rows_cap + row];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
@@ -479,7 +551,7 @@ extern "C" int fb_load_diag_gmm(fb_ctx *ctx, int slot, const float *weights, con
   FB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
   FB_CHECK_ARG(slot >= 0 && slot < FB_MAX_MODELS, "slot out of range");
   FB_CHECK_ARG(D == FB_DIM, "feature dimension must be 72");
-  FB_CHECK_ARG(C > 0 && C % FB_CHUNK_N == 0, "number of components must be a positive multiple of 128");
+  FB_CHECK_ARG(C > 0 && C % FB_CHUNK_N == 0 && C <= 32 * FB_CHUNK_N, "number of components must be a multiple of 128, at most 4096");
   FB_CHECK_ARG(weights && means_invvars && inv_vars && gconsts, "NULL parameter array");
   FbHostGmm &h = ctx->host_gmm[slot];
   h.weights.assign(weights, weights + C);
@@ -488,6 +560,23 @@ extern "C" int fb_load_diag_gmm(fb_ctx *ctx, int slot, const float *weights, con
   h.gconsts.assign(gconsts, gconsts + C);
   h.loaded = true;
   return FB_OK;
+}
+
+// fp16 hi/lo split helpers for the W image (values already scaled and multiplied by log2(e))
+static inline void put_split(std::vector<__half> &img, size_t hi_idx, size_t lo_off, double w) {
+  const __half hi = __float2half_rn((float)w);
+  const __half lo = __float2half_rn((float)(w - (double)__half2float(hi)));
+  img[hi_idx] = hi;
+  img[hi_idx + lo_off] = lo;
+}
+static inline void put_gconst3(std::vector<__half> &img, size_t idx, double gv) {
+  if (!(gv > -60000.0)) gv = -60000.0;         // zero-weight components: exp2 underflows to 0 anyway
+  if (gv > 60000.0) gv = 60000.0;
+  const __half g0 = __float2half_rn((float)gv);
+  const double r1 = gv - (double)__half2float(g0);
+  const __half g1 = __float2half_rn((float)r1);
+  const __half g2 = __float2half_rn((float)(r1 - (double)__half2float(g1)));
+  img[idx] = g0; img[idx + 1] = g1; img[idx + 2] = g2;
 }
 
 extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
@@ -516,57 +605,85 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
     ctx->tables_host.feat_scale[d] = (float)ldexp(1.0, -e);
   }
   ctx->tables_dirty = true;
+  // shared-variance mode: every model has exactly slot 0's inverse variances (MAP with --update-flags=m)
+  bool shared = n_models >= 2 && getenv("FB_GMM_NO_SHARED") == nullptr;
+  for (int m = 1; m < n_models && shared; ++m)
+    shared = ctx->host_gmm[m].inv_vars == g0.inv_vars;
+  ctx->gmm_shared = shared;
   const int n_stage = C / FB_STAGE_N;
-  const size_t stage_halfs = (size_t)(FB_W_HI_SLABS + FB_KSLABS) * FB_STAGE_N * 8;
-  const size_t img_halfs = (size_t)n_models * n_stage * stage_halfs;
-  std::vector<__half> img(img_halfs, __float2half_rn(0.f));
-  std::vector<float> gc2((size_t)n_models * C), gcn((size_t)n_models * C), wf((size_t)n_models * C * 2 * FB_DIM);
   const double log2e = 1.4426950408889634;
+  std::vector<float> gc2((size_t)n_models * C), gcn((size_t)n_models * C), wf((size_t)n_models * C * 2 * FB_DIM);
   for (int m = 0; m < n_models; ++m) {
     const FbHostGmm &h = ctx->host_gmm[m];
     for (int c = 0; c < C; ++c) {
       gc2[(size_t)m * C + c] = (float)((double)h.gconsts[c] * log2e);
       gcn[(size_t)m * C + c] = h.gconsts[c];
-      const int st = c / FB_STAGE_N, cc = c % FB_STAGE_N;
-      const size_t stage_base = ((size_t)m * n_stage + st) * stage_halfs;
-      {
-        // gconst * log2(e) as three fp16 terms in the extra hi slab (multiplied by the ones slab of A)
-        double gv = (double)h.gconsts[c] * log2e;
-        if (!(gv > -60000.0)) gv = -60000.0;         // zero-weight components: exp2 underflows to 0 anyway
-        if (gv > 60000.0) gv = 60000.0;
-        const __half g0 = __float2half_rn((float)gv);
-        const double r1 = gv - (double)__half2float(g0);
-        const __half g1 = __float2half_rn((float)r1);
-        const __half g2 = __float2half_rn((float)(r1 - (double)__half2float(g1)));
-        const size_t gb = stage_base + (size_t)FB_KSLABS * (FB_STAGE_N * 8) + cc * 8;
-        img[gb] = g0; img[gb + 1] = g1; img[gb + 2] = g2;
-      }
       for (int k = 0; k < 2 * FB_DIM; ++k) {
         const int d = (k < FB_DIM) ? k : k - FB_DIM;
-        const double s = ctx->tables_host.feat_scale[d];
-        const double raw = (k < FB_DIM) ? (double)h.means_invvars[(size_t)c * FB_DIM + d]
-                                        : -0.5 * (double)h.inv_vars[(size_t)c * FB_DIM + d];
-        wf[((size_t)m * C + c) * 2 * FB_DIM + k] = (float)raw;
-        const double w = ((k < FB_DIM) ? raw / s : raw / (s * s)) * log2e;
-        if (!(fabs(w) < 60000.0)) {
-          fb_set_error("model %d component %d dim %d: scaled weight %g exceeds the fp16 range", m, c, k, w);
-          return FB_ERR_UNSUPPORTED;
-        }
-        const __half hi = __float2half_rn((float)w);
-        const __half lo = __float2half_rn((float)(w - (double)__half2float(hi)));
-        const int slab = k >> 3, e = k & 7;
-        const size_t b = stage_base + (size_t)slab * (FB_STAGE_N * 8) + cc * 8 + e;
-        img[b] = hi;
-        img[b + (size_t)FB_W_HI_SLABS * FB_STAGE_N * 8] = lo;
+        wf[((size_t)m * C + c) * 2 * FB_DIM + k] = (k < FB_DIM) ? h.means_invvars[(size_t)c * FB_DIM + d] : -0.5f * h.inv_vars[(size_t)c * FB_DIM + d];
       }
     }
   }
+  // scaled weights in double: w1[m][c][d] = miv / s * log2e ; w2[c][d] = -0.5 iv / s^2 * log2e ; g[m][c] = gconst * log2e
+  auto w1 = [&](int m, int c, int d) {
+    return (double)ctx->host_gmm[m].means_invvars[(size_t)c * FB_DIM + d] / (double)ctx->tables_host.feat_scale[d] * log2e;
+  };
+  auto w2 = [&](int m, int c, int d) {
+    const double sc = ctx->tables_host.feat_scale[d];
+    return -0.5 * (double)ctx->host_gmm[m].inv_vars[(size_t)c * FB_DIM + d] / (sc * sc) * log2e;
+  };
+  auto gl = [&](int m, int c) { return (double)ctx->host_gmm[m].gconsts[c] * log2e; };
+  std::vector<__half> img;
+  const size_t slabW = (size_t)FB_STAGE_N * 8;                 // halfs per slab
+  bool range_err = false;
+  if (!shared) {
+    // [model][stage][hi 20 slabs | lo 20 slabs][64 cols][8]
+    const size_t stage_halfs = (size_t)2 * FB_W_HI_SLABS * slabW;
+    img.assign((size_t)n_models * n_stage * stage_halfs, __float2half_rn(0.f));
+    for (int m = 0; m < n_models; ++m)
+      for (int c = 0; c < C; ++c) {
+        const int st = c / FB_STAGE_N, cc = c % FB_STAGE_N;
+        const size_t sb = ((size_t)m * n_stage + st) * stage_halfs + (size_t)cc * 8;
+        const size_t lo_off = (size_t)FB_W_HI_SLABS * slabW;
+        for (int d = 0; d < FB_DIM; ++d) {
+          const double a1 = w1(m, c, d), a2 = w2(m, c, d);
+          if (!(fabs(a1) < 60000.0) || !(fabs(a2) < 60000.0)) range_err = true;
+          put_split(img, sb + (size_t)(d >> 3) * slabW + (d & 7), lo_off, a1);
+          put_split(img, sb + (size_t)(FB_SLAB_X2 + (d >> 3)) * slabW + (d & 7), lo_off, a2);
+        }
+        put_gconst3(img, sb + (size_t)FB_SLAB_ONES * slabW, gl(m, c));
+      }
+  } else {
+    // [stage][q = 0: x^2 part, q = 1+m: x part + gconst of model m][hi 10 slabs | lo 10 slabs][64 cols][8]
+    const size_t sub_halfs = (size_t)2 * 10 * slabW;
+    const int n_sub = n_models + 1;
+    img.assign((size_t)n_stage * n_sub * sub_halfs, __float2half_rn(0.f));
+    const size_t lo_off = (size_t)10 * slabW;
+    for (int c = 0; c < C; ++c) {
+      const int st = c / FB_STAGE_N, cc = c % FB_STAGE_N;
+      for (int q = 0; q < n_sub; ++q) {
+        const size_t sb = ((size_t)st * n_sub + q) * sub_halfs + (size_t)cc * 8;
+        for (int d = 0; d < FB_DIM; ++d) {
+          double v;
+          if (q == 0) v = w2(0, c, d);
+          else v = w1(q - 1, c, d);
+          if (!(fabs(v) < 60000.0)) range_err = true;
+          put_split(img, sb + (size_t)(d >> 3) * slabW + (d & 7), lo_off, v);
+        }
+        if (q >= 1) put_gconst3(img, sb + (size_t)9 * slabW, gl(q - 1, c));
+      }
+    }
+  }
+  if (range_err) {
+    fb_set_error("a scaled GMM weight exceeds the fp16 range (model dynamic range not supported by the split-fp16 kernel)");
+    return FB_ERR_UNSUPPORTED;
+  }
   int rc;
-  if ((rc = ctx->w_img.ensure(img_halfs))) return rc;
+  if ((rc = ctx->w_img.ensure(img.size()))) return rc;
   if ((rc = ctx->gconst2.ensure(gc2.size()))) return rc;
   if ((rc = ctx->gconst_nat.ensure(gcn.size()))) return rc;
   if ((rc = ctx->w_f32.ensure(wf.size()))) return rc;
-  FB_CUDA(cudaMemcpy(ctx->w_img.p, img.data(), img_halfs * sizeof(__half), cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(ctx->w_img.p, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
   FB_CUDA(cudaMemcpy(ctx->gconst2.p, gc2.data(), gc2.size() * sizeof(float), cudaMemcpyHostToDevice));
   FB_CUDA(cudaMemcpy(ctx->gconst_nat.p, gcn.data(), gcn.size() * sizeof(float), cudaMemcpyHostToDevice));
   FB_CUDA(cudaMemcpy(ctx->w_f32.p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -576,10 +693,12 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
   ctx->part.release();
   ctx->frame_ll.release();
   ctx->avg_ll.release();
+  ctx->batch_tag = -1;
   static bool attr_set = false;
   if (!attr_set) {
-    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
-    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
     attr_set = true;
   }
   return FB_OK;
@@ -599,11 +718,12 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     a.C = ctx->C;
     a.rows_cap = ctx->rows_cap;
     // upper bound on useful CTAs: one unit each
-    const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * ctx->n_models * nch;
+    const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * (ctx->gmm_shared ? 1 : ctx->n_models) * nch;
     int grid = ctx->num_sms;
     if (max_units < grid) grid = (int)max_units;
     a.ll_out = nullptr;
-    gmm_umma_kernel<false><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
+    if (ctx->gmm_shared) gmm_umma_kernel<false, true><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
+    else gmm_umma_kernel<false, false><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
   } else {
     dim3 grid(fb_div_up(ctx->total_frames, 32), ctx->n_models * nch);
     gmm_simt_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->a_img.p, ctx->w_f32.p, ctx->gconst_nat.p,
@@ -611,11 +731,12 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
                                                    ctx->n_models, ctx->C, ctx->rows_cap);
   }
   fb_prof_mark(ctx, 4);
-  dim3 g2(ctx->B, ctx->n_models);
-  gmm_reduce_kernel<<<g2, 128, 0, ctx->stream>>>(ctx->part.p, ctx->row_off.p, ctx->frame_ll.p, ctx->avg_ll.p,
-                                                 ctx->n_models, nch, ctx->rows_cap, done_flag);
+  gmm_frame_kernel<<<dim3(fb_div_up(ctx->total_frames, 128), ctx->n_models), 128, 0, ctx->stream>>>(
+      ctx->part.p, ctx->misc.p, ctx->frame_ll.p, nch, ctx->rows_cap, done_flag);
+  gmm_reduce_kernel<<<dim3(ctx->B, ctx->n_models), 128, 0, ctx->stream>>>(ctx->frame_ll.p, ctx->row_off.p, ctx->avg_ll.p,
+                                                                         ctx->n_models, ctx->rows_cap, done_flag);
   fb_prof_mark(ctx, 5);
-  ctx->launches += 2;
+  ctx->launches += 3;
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }
@@ -639,7 +760,8 @@ int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag) {
   const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * nch;
   int grid = ctx->num_sms;
   if (max_units < grid) grid = (int)max_units;
-  gmm_umma_kernel<true><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
+  FB_CHECK_ARG(!ctx->gmm_shared, "Gaussian selection needs the general W image");
+  gmm_umma_kernel<true, false><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
   fb_prof_mark(ctx, 4);
   ctx->launches += 1;
   FB_CUDA(cudaGetLastError());

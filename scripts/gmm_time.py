@@ -7,8 +7,8 @@ from fakebob_b200.engine import GmmEngine, to_audio_list
 r = np.random.default_rng(0)
 C = 2048
 gm = []
+iv = r.uniform(0.5, 4.0, (C, 72)).astype(np.float32)          # shared by all models (MAP mean-only adaptation)
 for m in range(6):
-    iv = r.uniform(0.5, 4.0, (C, 72)).astype(np.float32)
     mu = r.standard_normal((C, 72)).astype(np.float32)
     w = np.full(C, 1.0 / C, np.float32)
     gc = (np.log(w) - 0.5 * (72 * np.log(2 * np.pi) - np.log(iv).sum(1) + (mu * mu * iv).sum(1))).astype(np.float32)

@@ -133,3 +133,24 @@ def test_no_voiced_frames_raises(osi):
     # constant-energy audio: every frame has the same log-energy, none exceeds 5.5 + 0.5*mean when tiny
     with pytest.raises(FakebobLibraryError):
         osi.score([silent])
+
+
+def test_shared_variance_chain_matches_general_kernel(small_tree, monkeypatch):
+    """MAP mean-only speaker models share the UBM's variances, so scoring uses the accumulate-chain kernel; the
+    general per-model kernel (forced with FB_GMM_NO_SHARED) must give the same log-likelihoods."""
+    from fakebob_b200.engine import GmmEngine, to_audio_list
+    paths = [small_tree["ubm"]] + [m[2] for m in small_tree["models"]]
+    lst = to_audio_list([make_audio(91, 0), make_audio(92, 1, n=20000)])
+    shared = GmmEngine.from_files(paths)
+    a = shared.score_avg_ll(lst)
+    fa = shared.last_stages()["frame_ll"].copy()
+    monkeypatch.setenv("FB_GMM_NO_SHARED", "1")
+    general = GmmEngine.from_files(paths)
+    b = general.score_avg_ll(lst)
+    fb = general.last_stages()["frame_ll"].copy()
+    assert np.abs(fa - fb).max() < 1e-3
+    assert np.abs(a - b).max() < 3e-4
+    # the kernels' accumulation-order offsets are common to all models and cancel in the LLR scores
+    assert np.abs((a[:, 1:] - a[:, :1]) - (b[:, 1:] - b[:, :1])).max() < 5e-5
+    shared.close()
+    general.close()
