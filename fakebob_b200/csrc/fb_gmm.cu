@@ -281,15 +281,18 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const size_t stage = (size_t)ch * 2 + h;
+        // a bulk copy costs ~930 clk whatever its size (<= 40 KB) and copies of one SM do not overlap, so the shared
+        // mode fetches its 20 KB sub-stages two per ring entry
 #pragma unroll 1
-        for (int q = 0; q < n_sub; ++q) {
+        for (int q = 0; q < n_sub; q += kShared ? 2 : 1) {
           const uint32_t slot = cnt % kNumSlots;
           mbar_wait(bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
           if (elect_one()) {
-            const uint32_t bytes = kShared ? kWShBytes : kWStageBytes;
-            const size_t idx = kShared ? (stage * n_sub + q) : ((size_t)model * (g.C / FB_STAGE_N) + stage);
+            const uint32_t bytes = kShared ? ((q + 1 < n_sub) ? 2 * kWShBytes : kWShBytes) : kWStageBytes;
+            const size_t off = kShared ? (stage * n_sub + q) * (size_t)kWShBytes
+                                       : ((size_t)model * (g.C / FB_STAGE_N) + stage) * (size_t)kWStageBytes;
             mbar_expect_tx(bar_full + 8 * slot, bytes);
-            bulk_g2s(base + slot * kSlotBytes, reinterpret_cast<const uint8_t *>(g.w_img) + idx * bytes, bytes, bar_full + 8 * slot);
+            bulk_g2s(base + slot * kSlotBytes, reinterpret_cast<const uint8_t *>(g.w_img) + off, bytes, bar_full + 8 * slot);
           }
           __syncwarp();
           ++cnt;
@@ -329,8 +332,11 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
         for (int q = 0; q < n_sub; ++q) {
           const uint32_t slot = cnt % kNumSlots;
-          mbar_wait(bar_full + 8 * slot, (cnt / kNumSlots) & 1);
-          const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
+          const bool first_in_slot = !kShared || (q & 1) == 0;
+          const bool last_in_slot = !kShared || (q & 1) == 1 || q + 1 == n_sub;
+          if (first_in_slot) mbar_wait(bar_full + 8 * slot, (cnt / kNumSlots) & 1);
+          const uint32_t sub_off = (kShared && (q & 1)) ? kWShBytes : 0;
+          const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes + sub_off) & 0x3FFFFu) >> 4);
           const uint64_t w_lo = w_hi + (uint64_t)((kShared ? kWShHalfBytes : kWHalfBytes) >> 4);
           // shared mode: q = 0 is the x^2 sub-step, q >= 1 the x (+ gconst) sub-step of model q-1; all start from zero
           const uint32_t a_off = (kShared && q == 0) ? kTmemX2Cols : 0;
@@ -354,12 +360,12 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
                 }
               }
               tc_commit(bar_acc_full + 8 * abuf);
-              if (tile == 1) tc_commit(bar_empty + 8 * slot);
+              if (tile == 1 && last_in_slot) tc_commit(bar_empty + 8 * slot);
             }
             __syncwarp();
             ++job;
           }
-          ++cnt;
+          if (last_in_slot) ++cnt;
         }
       }
     }

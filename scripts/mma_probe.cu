@@ -64,6 +64,75 @@ __global__ void __launch_bounds__(128, 1) probe(int iters, long long *clk) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
+// jobs of J MMAs; after each job: commit to `bar2` (never waited) and try_wait once on an already-completed barrier
+template <int J>
+__global__ void __launch_bounds__(128, 1) probe_jobs(int jobs, int nwaits, long long *clk) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar, bar2, bar3;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar3)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t b_desc = make_desc(smem_u32(smem) + 8192, 64 * 16, 128);
+    long long t0 = clock64();
+    for (int j = 0; j < jobs; ++j) {
+      for (int w = 0; w < nwaits; ++w) {
+        uint32_t done;   // bar3 is fresh: waiting for parity 1 returns immediately (already-complete fast path)
+        do {
+          asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}" : "=r"(done) : "r"(smem_u32(&bar3)), "r"(1u) : "memory");
+        } while (!done);
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < J; ++k)
+          asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;}"
+                       ::"r"(tmem + 64 * (j % 3)), "r"(tmem + 256 + 8 * (k % 10)), "l"(b_desc), "r"(idesc), "r"(k ? 1u : 0u) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+      }
+      __syncwarp();
+    }
+    if (elect_one())
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    __syncwarp();
+    uint32_t done;
+    do {
+      asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    } while (!done);
+    if (threadIdx.x == 0) clk[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+template <int J>
+void run_jobs(long long *clk, int nwaits) {
+  const int jobs = 2000;
+  cudaFuncSetAttribute(probe_jobs<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  long long h[148];
+  for (int rep = 0; rep < 2; ++rep) { probe_jobs<J><<<148, 128, 48 * 1024>>>(jobs, nwaits, clk); cudaDeviceSynchronize(); }
+  cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
+  printf("jobs of %2d MMAs (N=64, A tmem), %d waits/job: clk/MMA %.1f  clk/job %.0f  err=%s\n", J, nwaits, avg / (jobs * (double)J), avg / jobs, cudaGetErrorString(cudaGetLastError()));
+}
 template <int N, bool TA>
 void run(long long *clk, const char *name) {
   const int iters = 2000;
@@ -88,5 +157,7 @@ int main() {
   run<64, true>(clk, "A tmem (TS)");
   run<128, true>(clk, "A tmem (TS)");
   run<256, true>(clk, "A tmem (TS)");
+  run_jobs<15>(clk, 0); run_jobs<15>(clk, 1); run_jobs<15>(clk, 2); run_jobs<15>(clk, 4);
+  run_jobs<30>(clk, 0); run_jobs<30>(clk, 2);
   return 0;
 }
