@@ -40,38 +40,69 @@ def env_int(name, default):
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons during the timed region (B200_PROFILING.md recipe), sampled through NVML
+    every 50 ms (falls back to the nvidia-smi query line when pynvml is unavailable).  The sampler is stopped before the
+    host-timed end-to-end legs: NVML queries take a driver lock that kernel launches also need."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []          # (sm_mhz, max_mhz, power_w, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
         self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        hw = bool(r & 0x8)            # nvmlClocksThrottleReasonHwSlowdown
+        hwt = bool(r & 0x40)          # HwThermalSlowdown
+        swt = bool(r & 0x20)          # SwThermalSlowdown
+        swp = bool(r & 0x4)           # SwPowerCap
+        self.samples.append((sm, self.max_mhz, pw, hw, hwt, swt, swp))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        p = [x.strip() for x in out.strip().split(",")]
+        if len(p) >= 7:
+            act = [x.lower().startswith("active") for x in p[3:7]]
+            self.samples.append((float(p[0]), float(p[1]), float(p[2]), act[0], act[1], act[2], act[3]))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.15)
+            time.sleep(0.02 if self.nvml is not None else 0.15)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = []
-        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
-            if any(s[3 + i].lower().startswith("active") for s in self.samples):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [name for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))
+                   if any(s[3 + i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "power_w_max": max(s[2] for s in self.samples), "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -161,6 +192,37 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bench_ivector(root, ubm_params, pre_model_dir, device, audio, iters=100):
+    """Informational: BASELINE.json configs[2] (iv_SV, 2048-mix full UBM, 400-dim i-vector, LDA 200 + PLDA, S=50)."""
+    from fakebob_b200 import synth
+    from fakebob_b200.engine import IvectorEngine
+    from fakebob_b200.FAKEBOB import FakeBob
+    from fakebob_b200.ivector_PLDA_SV import iv_SV
+    synth.build_ivector_params(root, ubm_params, R=400, L=200)
+    eng = IvectorEngine(pre_model_dir, device=device)
+    spk = synth.build_ivector_speakers(root, lambda w: eng.extract_ivectors([np.ascontiguousarray(w, dtype=np.int16)])[0],
+                                       lambda enrolled, test: np.arange(len(test), dtype=np.float64)[:, None] + np.zeros((1, len(enrolled))),
+                                       n_speakers=1, n_samples=N_SAMPLES, n_znorm_utts=2)
+    eng.close()
+    model = iv_SV(os.path.join(root, "iv-sv"), spk["models"][0], pre_model_dir=pre_model_dir, device=device)
+    fb = FakeBob("SV", "untargeted", model, max_iter=30, samples_per_draw=S_DRAW, seed=1, verbose=False)
+    fb.attack(audio, None, threshold=1e9)
+    fb = FakeBob("SV", "untargeted", model, max_iter=iters, samples_per_draw=S_DRAW, seed=1, verbose=False)
+    t0 = time.perf_counter()
+    fb.attack(audio, None, threshold=1e9)
+    dt = time.perf_counter() - t0
+    e = model._engine
+    e.profile(True)
+    fb = FakeBob("SV", "untargeted", model, max_iter=10, samples_per_draw=S_DRAW, seed=1, verbose=False)
+    fb.attack(audio, None, threshold=1e9)
+    prof = e.profile_read()
+    e.profile(False)
+    return {"workload": "C3: iv_SV, 2048-mix full UBM, 400-dim i-vector, LDA 200 + PLDA, samples_per_draw=50, 5 s @ 16 kHz",
+            "iters_per_s_attack_api": fb.max_iter and iters / dt, "ms_per_iter": dt / iters * 1e3,
+            "published_reference": "README.md:112-113: ~12 s / iteration (ivector-PLDA)",
+            "stage_ms": {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1]}}
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -199,6 +261,7 @@ def main():
         root = tempfile.mkdtemp(prefix="fakebob_bench_")
         tree = build_workload_gpu(root, local_rank)
         holder[0] = {k: tree[k] for k in ("pre_model_dir", "model_dir", "ubm", "spk_ids", "models")}
+        ubm_params, bench_root = tree["ubm_params"], root
     if multi:
         dist.broadcast_object_list(holder, src=0)
     tree = holder[0]
@@ -252,6 +315,8 @@ def main():
         torch.cuda.synchronize()
         barrier()
         ms_hot = e0.elapsed_time(e1)
+        sampler.stop_flag = True
+        sampler.join(timeout=2.0)
         it_done, stopped = eng.nes_status()
         assert not stopped and it_done == W + 2 * K, (it_done, stopped)
         rows = eng.voiced_rows()
@@ -294,7 +359,6 @@ def main():
         fb3.attack(audio, None, threshold=theta)
         t_attack = time.perf_counter() - t0
         barrier()
-        sampler.stop_flag = True
 
     def max_over_ranks(x):
         if not multi:
@@ -349,6 +413,11 @@ def main():
             "stage_ms": {k: (v[0] / max(v[1], 1)) for k, v in prof.items()},
             "clocks": clocks,
         }
+        if world == 1 and os.environ.get("FB_BENCH_SKIP_IV") is None:
+            try:
+                line["extra_config_C3"] = bench_ivector(bench_root, ubm_params, tree["pre_model_dir"], local_rank, audio)
+            except Exception as e:                       # informational only: never break the contract line
+                line["extra_config_C3"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.perf_counter()
             ips, sample, cores = time_oracle(tree, audio, steps=2, warmup=1)

@@ -109,9 +109,36 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 #define MFCC_WARPS 8
-#define FFT_PAD(i) ((i) + ((i) >> 2))          // float2 index padding: radix-4 Stockham stores become conflict-free
-#define FFT_BUF 320                             // 256 + 64 padding
+#define FFT_PAD(i) ((i) + ((i) >> 3))          // float2 index padding (one slot per 8): stores of all stages stay <= 3 wavefronts
+#define FFT_BUF 320                             // 256 + 32 padding, rounded up
 
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }            // -i * a
+
+// forward 4-point DFT, natural order
+__device__ __forceinline__ void dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3) {
+  const float2 s0 = cadd(v0, v2), s1 = csub(v0, v2), s2 = cadd(v1, v3), s3 = mul_mi(csub(v1, v3));
+  v0 = cadd(s0, s2); v1 = cadd(s1, s3); v2 = csub(s0, s2); v3 = csub(s1, s3);
+}
+// forward 8-point DFT, natural order: y[r] = a[r] + W8^r b[r], y[r+4] = a[r] - W8^r b[r]
+__device__ __forceinline__ void dft8(float2 *u) {
+  float2 a0 = u[0], a1 = u[2], a2 = u[4], a3 = u[6], b0 = u[1], b1 = u[3], b2 = u[5], b3 = u[7];
+  dft4(a0, a1, a2, a3);
+  dft4(b0, b1, b2, b3);
+  const float h = 0.70710678118654752f;
+  const float2 t1 = make_float2(h * (b1.x + b1.y), h * (b1.y - b1.x));        // b1 * (1 - i)/sqrt2
+  const float2 t2 = mul_mi(b2);                                                // b2 * -i
+  const float2 t3 = make_float2(h * (b3.y - b3.x), -h * (b3.x + b3.y));       // b3 * (-1 - i)/sqrt2
+  u[0] = cadd(a0, b0); u[4] = csub(a0, b0);
+  u[1] = cadd(a1, t1); u[5] = csub(a1, t1);
+  u[2] = cadd(a2, t2); u[6] = csub(a2, t2);
+  u[3] = cadd(a3, t3); u[7] = csub(a3, t3);
+}
+
+// One warp per frame.  Lane l holds samples 128 r + 4 l + k (r = 0..3 rounds, k = 0..3), i.e. exactly the inputs of the
+// two first-stage radix-4 butterflies j = 2l, 2l+1 of the 256-point complex FFT (256 = 4 x 8 x 8), so framing, DC removal,
+// pre-emphasis, windowing and the first FFT stage never touch shared memory.
 __global__ void __launch_bounds__(MFCC_WARPS * 32)
 mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_off,
             const int *__restrict__ frame_off, const FbTables *__restrict__ tb,
@@ -131,97 +158,115 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
   const int64_t w0 = wave_off[b];
   const int n_samp = (int)(wave_off[b + 1] - w0);
   const int16_t *w = wave + w0;
-  float *bufA = reinterpret_cast<float *>(s_buf[warp][0]);
-  float *bufB = reinterpret_cast<float *>(s_buf[warp][1]);
+  float2 *bufA = s_buf[warp][0];
+  float2 *bufB = s_buf[warp][1];
 
-  // ---- extract window (snip_edges=false, reflected edges), DC removal, raw log-energy
+  // ---- extract window (snip_edges=false, reflected edges)
   const int start = FB_FRAME_SHIFT * t + FB_FRAME_SHIFT / 2 - FB_FRAME_LEN / 2;
-  float x[13];
+  float x[4][4];
+  const bool interior = start >= 0 && start + FB_FRAME_LEN <= n_samp && ((w0 + start) & 3) == 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i0 = 128 * r + 4 * lane;
+    if (i0 < FB_FRAME_LEN) {
+      if (interior) {
+        const short4 q = *reinterpret_cast<const short4 *>(w + start + i0);
+        x[r][0] = (float)q.x; x[r][1] = (float)q.y; x[r][2] = (float)q.z; x[r][3] = (float)q.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int sidx = start + i0 + k;
+          while (sidx < 0 || sidx >= n_samp) sidx = (sidx < 0) ? (-sidx - 1) : (2 * n_samp - 1 - sidx);
+          x[r][k] = (float)w[sidx];
+        }
+      }
+    } else {
+      x[r][0] = x[r][1] = x[r][2] = x[r][3] = 0.f;
+    }
+  }
+  // ---- DC removal, raw log-energy
   float sum = 0.f;
 #pragma unroll
-  for (int q = 0; q < 13; ++q) {
-    int i = lane + 32 * q;
-    float v = 0.f;
-    if (i < FB_FRAME_LEN) {
-      int s = start + i;
-      while (s < 0 || s >= n_samp) s = (s < 0) ? (-s - 1) : (2 * n_samp - 1 - s);
-      v = (float)w[s];
-    }
-    x[q] = v;
-    sum += v;
-  }
+  for (int r = 0; r < 4; ++r) sum += (x[r][0] + x[r][1]) + (x[r][2] + x[r][3]);
   sum = warp_sum(sum);                       // exact: integers, |sum| < 2^24
   const float mean = sum / (float)FB_FRAME_LEN;
   float e = 0.f;
 #pragma unroll
-  for (int q = 0; q < 13; ++q) {
-    int i = lane + 32 * q;
-    if (i < FB_FRAME_LEN) {
-      x[q] -= mean;
-      e += x[q] * x[q];
-      bufA[i] = x[q];
+  for (int r = 0; r < 4; ++r)
+    if (128 * r + 4 * lane < FB_FRAME_LEN) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { x[r][k] -= mean; e += x[r][k] * x[r][k]; }
     }
-  }
   e = warp_sum(e);
   const float log_energy = logf(fmaxf(e, 1.1920928955078125e-07f));
-  __syncwarp();
-  // ---- pre-emphasis + Povey window, zero-padded to 512 -> bufB as complex z[n] = x[2n] + i x[2n+1] (padded index)
+  // ---- pre-emphasis (needs the previous sample: neighbouring lane / previous round) + Povey window
   const float pe = tb->preemph;
+  float y[4][4];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const int i = lane + 32 * q;
-    float v = 0.f;
-    if (q < 13 && i < FB_FRAME_LEN) {
-      const float prev = bufA[i > 0 ? i - 1 : 0];
-      v = (x[q < 13 ? q : 0] - pe * prev) * __ldg(&tb->window[i]);
+  for (int r = 0; r < 4; ++r) {
+    const float up = __shfl_up_sync(0xffffffffu, x[r][3], 1);
+    const float wrap = __shfl_sync(0xffffffffu, x[r > 0 ? r - 1 : 0][3], 31);
+    const float prev0 = (lane > 0) ? up : ((r > 0) ? wrap : x[0][0]);
+    const int i0 = 128 * r + 4 * lane;
+    if (i0 < FB_FRAME_LEN) {
+      const float4 wn = __ldg(reinterpret_cast<const float4 *>(&tb->window[i0]));
+      y[r][0] = (x[r][0] - pe * prev0) * wn.x;
+      y[r][1] = (x[r][1] - pe * x[r][0]) * wn.y;
+      y[r][2] = (x[r][2] - pe * x[r][1]) * wn.z;
+      y[r][3] = (x[r][3] - pe * x[r][2]) * wn.w;
+    } else {
+      y[r][0] = y[r][1] = y[r][2] = y[r][3] = 0.f;
     }
-    bufB[2 * FFT_PAD(i >> 1) + (i & 1)] = v;
+  }
+  // ---- FFT stage A (radix 4, Ns = 1), in registers: butterflies j = 2 lane and 2 lane + 1; out[4 j + r]
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float2 v0 = make_float2(y[0][2 * h], y[0][2 * h + 1]), v1 = make_float2(y[1][2 * h], y[1][2 * h + 1]);
+    float2 v2 = make_float2(y[2][2 * h], y[2][2 * h + 1]), v3 = make_float2(y[3][2 * h], y[3][2 * h + 1]);
+    dft4(v0, v1, v2, v3);
+    const int o = 4 * (2 * lane + h);
+    bufA[FFT_PAD(o)] = v0; bufA[FFT_PAD(o + 1)] = v1; bufA[FFT_PAD(o + 2)] = v2; bufA[FFT_PAD(o + 3)] = v3;
   }
   __syncwarp();
-  // ---- 256-point complex FFT, radix-4 Stockham, stages Ns = 1, 4, 16, 64
-  float2 *in = reinterpret_cast<float2 *>(bufB);
-  float2 *out = reinterpret_cast<float2 *>(bufA);
+  // ---- stage B (radix 8, Ns = 4): butterfly j = lane, k = j & 3, twiddle exp(-2 pi i r k / 32)
+  {
+    const int k = lane & 3;
+    float2 u[8];
 #pragma unroll
-  for (int ls = 0; ls < 8; ls += 2) {
-    const int Ns = 1 << ls;
+    for (int r = 0; r < 8; ++r) u[r] = bufA[FFT_PAD(lane + 32 * r)];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = lane + 32 * h;
-      const int k = j & (Ns - 1);
-      const int tws = (k << (7 - ls));       // k * 512 / (4 Ns) in the 512-entry table
-      float2 v0 = in[FFT_PAD(j)], v1 = in[FFT_PAD(j + 64)], v2 = in[FFT_PAD(j + 128)], v3 = in[FFT_PAD(j + 192)];
-      if (ls > 0) {
-        v1 = cmul(v1, s_tw[tws]);
-        v2 = cmul(v2, s_tw[2 * tws]);
-        v3 = cmul(v3, s_tw[3 * tws]);
-      }
-      float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-      float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-      float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-      float2 d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
-      float2 a3 = make_float2(d13.y, -d13.x);                 // -i * (v1 - v3)
-      const int j0 = ((j - k) << 2) + k;
-      out[FFT_PAD(j0)] = make_float2(a0.x + a2.x, a0.y + a2.y);
-      out[FFT_PAD(j0 + Ns)] = make_float2(a1.x + a3.x, a1.y + a3.y);
-      out[FFT_PAD(j0 + 2 * Ns)] = make_float2(a0.x - a2.x, a0.y - a2.y);
-      out[FFT_PAD(j0 + 3 * Ns)] = make_float2(a1.x - a3.x, a1.y - a3.y);
-    }
-    __syncwarp();
-    float2 *tmp = in; in = out; out = tmp;
+    for (int r = 1; r < 8; ++r) u[r] = cmul(u[r], s_tw[r * k * 16]);
+    dft8(u);
+    const int j0 = ((lane >> 2) << 5) + k;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) bufB[FFT_PAD(j0 + 4 * r)] = u[r];
   }
-  // result Z in `in` (= bufB after 4 swaps); power spectrum bins 0..255 -> `out` viewed as float[256]
-  float *pw = reinterpret_cast<float *>(out);
+  __syncwarp();
+  // ---- stage C (radix 8, Ns = 32): k = lane, twiddle exp(-2 pi i r k / 256); out[k + 32 r]
+  {
+    float2 u[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) u[r] = bufB[FFT_PAD(lane + 32 * r)];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) u[r] = cmul(u[r], s_tw[r * lane * 2]);
+    dft8(u);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) bufA[FFT_PAD(lane + 32 * r)] = u[r];
+  }
+  __syncwarp();
+  // ---- real-FFT post-processing -> power spectrum bins 0..255 in bufB viewed as float[256]
+  float *pw = reinterpret_cast<float *>(bufB);
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const int k = lane + 32 * m;
-    float2 zk = in[FFT_PAD(k)];
-    float2 zc = in[FFT_PAD((256 - k) & 255)];
+    const float2 zk = bufA[FFT_PAD(k)];
+    float2 zc = bufA[FFT_PAD((256 - k) & 255)];
     zc.y = -zc.y;
-    float2 ev = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-    float2 df = make_float2(zk.x - zc.x, zk.y - zc.y);
-    float2 od = make_float2(0.5f * df.y, -0.5f * df.x);       // -i/2 * (zk - zc)
-    float2 xo = cmul(od, s_tw[k]);
-    float re = ev.x + xo.x, im = ev.y + xo.y;
+    const float2 ev = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+    const float2 df = csub(zk, zc);
+    const float2 od = make_float2(0.5f * df.y, -0.5f * df.x);       // -i/2 * (zk - zc)
+    const float2 xo = cmul(od, s_tw[k]);
+    const float re = ev.x + xo.x, im = ev.y + xo.y;
     pw[k] = re * re + im * im;
   }
   __syncwarp();
@@ -230,6 +275,7 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
   if (lane < tb->num_mel) {
     const int st = tb->mel_start[lane], ln = tb->mel_len[lane];
     float acc = 0.f;
+#pragma unroll 4
     for (int i = 0; i < ln; ++i) acc += __ldg(&tb->mel_w_t[i][lane]) * pw[st + i];
     lm = logf(fmaxf(acc, 1.1920928955078125e-07f));
   }
@@ -238,6 +284,7 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
   if (lane < FB_NCEPS) {
     float c = 0.f;
     const int nm = tb->num_mel;
+#pragma unroll 6
     for (int m = 0; m < nm; ++m) c += __ldg(&tb->dct_t[m][lane]) * s_lm[warp][m];
     c *= __ldg(&tb->lifter[lane]);
     if (lane == 0) c = log_energy;

@@ -842,7 +842,7 @@ extern "C" int fb_set_enrolled_ivectors(fb_ctx *ctx, const float *enrolled, int 
   return FB_OK;
 }
 
-static int iv_reserve(fb_ctx *ctx) {
+int fb_ivector_reserve(fb_ctx *ctx) {
   FbIvector *v = ctx->iv;
   const int B = ctx->B;
   int rc;
@@ -866,7 +866,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   FB_CHECK_ARG(v && v->have_ubm && v->have_ie, "full UBM and i-vector extractor must be loaded");
   FB_CHECK_ARG(!with_plda || (v->have_backend && v->K > 0), "PLDA back-end / enrolled speakers missing");
   int rc;
-  if ((rc = iv_reserve(ctx))) return rc;
+  if ((rc = fb_ivector_reserve(ctx))) return rc;
   const int B = ctx->B;
   const int rows = ctx->total_frames;           // upper bound of the voiced rows (device knows the exact count)
   if ((rc = fb_run_gmm_store(ctx, v->ll.p, done_flag))) return rc;

@@ -26,3 +26,4 @@ struct FbIvector {
 
 void fb_ivector_destroy(fb_ctx *ctx);
 int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda);
+int fb_ivector_reserve(fb_ctx *ctx);      // allocate the per-batch workspace (never inside a stream capture)

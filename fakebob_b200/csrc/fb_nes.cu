@@ -330,6 +330,8 @@ static int nes_claim_batch(fb_ctx *ctx) {
     if ((rc = fb_reserve_batch(ctx, s->B_local, s->offsets.data()))) return rc;
     ctx->batch_tag = 1;
   }
+  if (ctx->arch == 1 && ctx->iv)
+    if ((rc = fb_ivector_reserve(ctx))) return rc;       // before any graph capture
   if (s->graph_exec && s->graph_epoch != fb_alloc_epoch()) {
     cudaGraphExecDestroy(s->graph_exec);
     cudaGraphDestroy(s->graph);
