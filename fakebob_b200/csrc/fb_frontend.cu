@@ -298,7 +298,7 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
 __global__ void __launch_bounds__(256)
 vad_scan_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_off, const FbTables *__restrict__ tb,
                 int *__restrict__ vrank, int *__restrict__ nvoiced, int *__restrict__ row_off,
-                int *__restrict__ misc, int B, const int *__restrict__ done_flag) {
+                int *__restrict__ misc, int B, int c0_cap, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
   __shared__ double s_red[8];
   __shared__ int s_wtot[8];
@@ -307,8 +307,14 @@ vad_scan_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_of
   const int b = blockIdx.x;
   const int f0 = frame_off[b];
   const int T = frame_off[b + 1] - f0;
+  extern __shared__ float s_c0[];                       // [min(T, cap)] log-energies of this utterance
+  const int cap = c0_cap;
   double s = 0.0;
-  for (int t = tid; t < T; t += 256) s += (double)mfcc[(int64_t)(f0 + t) * FB_NCEPS];
+  for (int t = tid; t < T; t += 256) {
+    const float v = mfcc[(int64_t)(f0 + t) * FB_NCEPS];
+    if (t < cap) s_c0[t] = v;
+    s += (double)v;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) s_red[warp] = s;
@@ -329,7 +335,8 @@ vad_scan_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_of
       for (int t2 = t - ctx; t2 <= t + ctx; ++t2)
         if (t2 >= 0 && t2 < T) {
           den++;
-          num += (mfcc[(int64_t)(f0 + t2) * FB_NCEPS] > thr) ? 1 : 0;
+          const float c0v = (t2 < cap) ? s_c0[t2] : mfcc[(int64_t)(f0 + t2) * FB_NCEPS];
+          num += (c0v > thr) ? 1 : 0;
         }
       v = ((float)num >= __fmul_rn((float)den, prop)) ? 1 : 0;
     }
@@ -395,7 +402,7 @@ vad_scan_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_of
 // One CTA per (utterance, output slab): slab sl = 3*order + cepstra-group holds dims d = 24*order + 8*cg + 0..7,
 // so each CTA owns x-slab sl and x^2-slab 9+sl and every store is a full 16-byte row chunk.
 // ------------------------------------------------------------------------------------------------
-#define FEATS_THREADS 256
+#define FEATS_THREADS 512
 #define FEATS_NSEG (FEATS_THREADS / 8)
 
 __device__ __forceinline__ void split_pack8(const float *v, uint4 &hi, uint4 &lo) {
@@ -423,11 +430,30 @@ feats_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_off, 
   const int b = blockIdx.y;
   const int f0 = frame_off[b];
   const int T = frame_off[b + 1] - f0;
-  // P[(T+1)][8] float64 prefix sums, raw[T][8] float features of this slab
+  // issue every small global read now so their latencies overlap (they are consumed in the last phase)
+  const int W = tb->cmn_window;
+  const int r0 = row_off[b];
+  float scale[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) scale[i] = tb->feat_scale[ord * FB_NCEPS + cg * 8 + i];
+  const int vr_first = (threadIdx.x < T) ? vrank[f0 + threadIdx.x] : -1;
+  // P[(T+1)][8] float64 prefix sums, raw[T][8] float features of this slab, stat[T][8] the cepstra group's statics
   double *P = use_smem ? s_dyn : pre_global + ((size_t)(f0 + b) * 9 + (size_t)sl * (T + 1)) * 8;
   float *raw = use_smem ? reinterpret_cast<float *>(s_dyn + (size_t)(T + 1) * 8)
                         : raw_global + ((size_t)f0 * 9 + (size_t)sl * T) * 8;
-  const float *mf = mfcc + (size_t)f0 * FB_NCEPS + cg * 8;
+  const float *mfg = mfcc + (size_t)f0 * FB_NCEPS + cg * 8;
+  const float *mf = mfg;
+  int mstride = FB_NCEPS;
+  if (use_smem) {
+    float *stat = reinterpret_cast<float *>(P);       // aliases the prefix-sum area, which is only written after phase A
+    for (int idx = threadIdx.x; idx < T * 2; idx += blockDim.x) {          // 2 float4 per frame
+      const int t = idx >> 1, h = idx & 1;
+      reinterpret_cast<float4 *>(stat)[idx] = *reinterpret_cast<const float4 *>(mfg + (size_t)t * FB_NCEPS + 4 * h);
+    }
+    __syncthreads();
+    mf = stat;
+    mstride = 8;
+  }
   // ---- phase A: this slab's static / delta / delta-delta values, float accumulation in Kaldi's tap order
   float sc1[7], sc2[13];
 #pragma unroll
@@ -438,17 +464,17 @@ feats_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_off, 
     const int t = idx >> 3, ci = idx & 7;
     float v;
     if (ord == 0) {
-      v = mf[t * FB_NCEPS + ci];
+      v = mf[t * mstride + ci];
     } else if (ord == 1) {
       v = 0.f;
 #pragma unroll
       for (int j = -3; j <= 3; ++j)
-        if (sc1[j + 3] != 0.f) v = __fadd_rn(v, __fmul_rn(sc1[j + 3], mf[min(max(t + j, 0), T - 1) * FB_NCEPS + ci]));
+        if (sc1[j + 3] != 0.f) v = __fadd_rn(v, __fmul_rn(sc1[j + 3], mf[min(max(t + j, 0), T - 1) * mstride + ci]));
     } else {
       v = 0.f;
 #pragma unroll
       for (int j = -6; j <= 6; ++j)
-        if (sc2[j + 6] != 0.f) v = __fadd_rn(v, __fmul_rn(sc2[j + 6], mf[min(max(t + j, 0), T - 1) * FB_NCEPS + ci]));
+        if (sc2[j + 6] != 0.f) v = __fadd_rn(v, __fmul_rn(sc2[j + 6], mf[min(max(t + j, 0), T - 1) * mstride + ci]));
     }
     raw[idx] = v;
   }
@@ -471,13 +497,8 @@ feats_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_off, 
   if (T == 0) return;
   __syncthreads();
   // ---- phase C: x - window mean, scale, split, pack; one thread per voiced frame (8 dims = one 16-byte chunk)
-  const int W = tb->cmn_window;
-  const int r0 = row_off[b];
-  float scale[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) scale[i] = tb->feat_scale[ord * FB_NCEPS + cg * 8 + i];
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const int r = vrank[f0 + t];
+    const int r = (t == (int)threadIdx.x) ? vr_first : vrank[f0 + t];
     if (r < 0) continue;
     int ws = t - W / 2, we = ws + W;
     if (ws < 0) { we -= ws; ws = 0; }
@@ -595,8 +616,9 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   mfcc_kernel<<<g1, MFCC_WARPS * 32, 0, ctx->stream>>>(ctx->wave.p, ctx->wave_off.p, ctx->frame_off.p, ctx->tables_dev,
                                                        ctx->mfcc.p, done_flag);
   fb_prof_mark(ctx, 1);
-  vad_scan_kernel<<<B, 256, 0, ctx->stream>>>(ctx->mfcc.p, ctx->frame_off.p, ctx->tables_dev, ctx->vrank.p,
-                                              ctx->nvoiced.p, ctx->row_off.p, ctx->misc.p, B, done_flag);
+  const int c0_cap = ctx->max_frames < 8192 ? ctx->max_frames : 8192;
+  vad_scan_kernel<<<B, 256, (size_t)c0_cap * sizeof(float), ctx->stream>>>(ctx->mfcc.p, ctx->frame_off.p, ctx->tables_dev, ctx->vrank.p,
+                                                                          ctx->nvoiced.p, ctx->row_off.p, ctx->misc.p, B, c0_cap, done_flag);
   fb_prof_mark(ctx, 2);
   const size_t smem = fb_feats_smem_bytes(ctx->max_frames);
   const int use_smem = smem <= FB_FEATS_SMEM_MAX;

@@ -38,15 +38,17 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// Box-Muller in float32 on 23-bit uniforms (every integer -> float step is exact; logf / sincosf are the accurate
+// <= 2 ulp library versions).  The normal deviates are float32 values widened to float64 for the state arithmetic.
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, double &z0, double &z1) {
-  const double ua = __dmul_rn(__dadd_rn((double)xa, 0.5), 2.3283064365386963e-10);
-  const double ub = __dmul_rn(__dadd_rn((double)xb, 0.5), 2.3283064365386963e-10);
-  const double rad = sqrt(__dmul_rn(-2.0, log(ua)));
-  const double ang = __dmul_rn(6.283185307179586, ub);
-  double sn, cs;
-  sincos(ang, &sn, &cs);
-  z0 = __dmul_rn(rad, cs);
-  z1 = __dmul_rn(rad, sn);
+  const float ua = __fmul_rn(__fadd_rn((float)(xa >> 9), 0.5f), 1.1920928955078125e-07f);    // (k + 0.5) * 2^-23
+  const float ub = __fmul_rn(__fadd_rn((float)(xb >> 9), 0.5f), 1.1920928955078125e-07f);
+  const float rad = __fsqrt_rn(__fmul_rn(-2.0f, logf(ua)));
+  const float ang = __fmul_rn(6.2831855f, ub);
+  float sn, cs;
+  sincosf(ang, &sn, &cs);
+  z0 = (double)__fmul_rn(rad, cs);
+  z1 = (double)__fmul_rn(rad, sn);
 }
 
 __device__ __forceinline__ int16_t quantise(double v) {
@@ -63,11 +65,14 @@ perturb_kernel(FbNesDev st, int16_t *__restrict__ wave, int64_t stride, int phil
   const int64_t n0 = g * 4;
   if (n0 >= st.N) return;
   const int nv = (int)min((int64_t)4, st.N - n0);
+  const bool vec = nv == 4 && (st.N & 3) == 0 && (stride & 3) == 0;     // rows stay 8-byte (int16) / 32-byte (f64) aligned
   double a[4];
   for (int i = 0; i < nv; ++i) a[i] = st.adver[n0 + i];
   const int bclean = st.has_clean ? 1 : 0;
-  if (bclean && blockIdx.y == 0)
-    for (int i = 0; i < nv; ++i) wave[n0 + i] = quantise(a[i]);
+  if (bclean && blockIdx.y == 0) {
+    if (vec) *reinterpret_cast<short4 *>(wave + n0) = make_short4(quantise(a[0]), quantise(a[1]), quantise(a[2]), quantise(a[3]));
+    else for (int i = 0; i < nv; ++i) wave[n0 + i] = quantise(a[i]);
+  }
   const unsigned long long draw = st.state_u64[0];
   for (int j = blockIdx.y; j < st.pairs_local; j += gridDim.y) {
     double z[4];
@@ -77,16 +82,29 @@ perturb_kernel(FbNesDev st, int16_t *__restrict__ wave, int64_t stride, int phil
                     (uint32_t)st.seed, (uint32_t)(st.seed >> 32), r);
       box_muller(r[0], r[1], z[0], z[1]);
       box_muller(r[2], r[3], z[2], z[3]);
-      for (int i = 0; i < nv; ++i) st.noise[(int64_t)j * st.N + n0 + i] = z[i];
+      double *np_ = st.noise + (int64_t)j * st.N + n0;
+      if (vec) {                                      // one full 32-byte sector per lane
+        reinterpret_cast<double2 *>(np_)[0] = make_double2(z[0], z[1]);
+        reinterpret_cast<double2 *>(np_)[1] = make_double2(z[2], z[3]);
+      } else {
+        for (int i = 0; i < nv; ++i) np_[i] = z[i];
+      }
     } else {
       for (int i = 0; i < nv; ++i) z[i] = st.noise[(int64_t)j * st.N + n0 + i];
     }
     int16_t *wp = wave + (int64_t)(bclean + j) * stride + n0;
     int16_t *wm = wave + (int64_t)(bclean + st.pairs_local + j) * stride + n0;
+    int16_t qp[4], qm[4];
     for (int i = 0; i < nv; ++i) {
       const double t = __dmul_rn(st.sigma, z[i]);
-      wp[i] = quantise(__dadd_rn(t, a[i]));
-      wm[i] = quantise(__dadd_rn(-t, a[i]));
+      qp[i] = quantise(__dadd_rn(t, a[i]));
+      qm[i] = quantise(__dadd_rn(-t, a[i]));
+    }
+    if (vec) {                                        // 8-byte stores: a warp writes 256 contiguous bytes
+      *reinterpret_cast<short4 *>(wp) = make_short4(qp[0], qp[1], qp[2], qp[3]);
+      *reinterpret_cast<short4 *>(wm) = make_short4(qm[0], qm[1], qm[2], qm[3]);
+    } else {
+      for (int i = 0; i < nv; ++i) { wp[i] = qp[i]; wm[i] = qm[i]; }
     }
   }
 }
@@ -95,31 +113,39 @@ perturb_kernel(FbNesDev st, int16_t *__restrict__ wave, int64_t stride, int phil
 // numpy pairwise summation (pairwise_sum_DOUBLE): blocks of <=128 with 8 accumulators, recursive halves above.
 // ------------------------------------------------------------------------------------------------
 template <typename F>
-__device__ double np_pairwise(const F &get, int lo, int n) {
+__device__ __forceinline__ double np_pairwise_block(const F &get, int lo, int n) {     // n <= 128
   if (n < 8) {
     double r = 0.0;
     for (int i = 0; i < n; ++i) r = __dadd_rn(r, get(lo + i));
     return r;
   }
-  if (n <= 128) {
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = get(lo + j);
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], get(lo + i + j));
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __dadd_rn(res, get(lo + i));
-    return res;
+  double r0 = get(lo), r1 = get(lo + 1), r2 = get(lo + 2), r3 = get(lo + 3);
+  double r4 = get(lo + 4), r5 = get(lo + 5), r6 = get(lo + 6), r7 = get(lo + 7);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+    r0 = __dadd_rn(r0, get(lo + i));     r1 = __dadd_rn(r1, get(lo + i + 1));
+    r2 = __dadd_rn(r2, get(lo + i + 2)); r3 = __dadd_rn(r3, get(lo + i + 3));
+    r4 = __dadd_rn(r4, get(lo + i + 4)); r5 = __dadd_rn(r5, get(lo + i + 5));
+    r6 = __dadd_rn(r6, get(lo + i + 6)); r7 = __dadd_rn(r7, get(lo + i + 7));
   }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+  for (; i < n; ++i) res = __dadd_rn(res, get(lo + i));
+  return res;
+}
+
+template <typename F>
+__device__ __noinline__ double np_pairwise_rec(const F &get, int lo, int n) {          // n > 128: numpy's recursive halves
+  if (n <= 128) return np_pairwise_block(get, lo, n);
   int n2 = n / 2;
   n2 -= n2 % 8;
-  const double a = np_pairwise(get, lo, n2);
-  const double b = np_pairwise(get, lo + n2, n - n2);
+  const double a = np_pairwise_rec(get, lo, n2);
+  const double b = np_pairwise_rec(get, lo + n2, n - n2);
   return __dadd_rn(a, b);
+}
+
+template <typename F>
+__device__ __forceinline__ double np_pairwise(const F &get, int lo, int n) {
+  return (n <= 128) ? np_pairwise_block(get, lo, n) : np_pairwise_rec(get, lo, n);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,6 +315,52 @@ nes_update_kernel(FbNesDev st, int mode, int use_state_lr, double lr_arg) {
   }
   if (mode == 3 || mode == 1) return;
   // next iteration's pre-update distance = max |audio - adver| now
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dist = fmax(dist, __shfl_xor_sync(0xffffffffu, dist, o));
+  if ((threadIdx.x & 31) == 0 && dist > 0.0)
+    atomicMax(&st.dist_bits[st.flags[1]], (unsigned long long)__double_as_longlong(dist));
+}
+
+// Single-GPU gradient + update with 8 lanes per sample: numpy's pairwise block (8 <= S <= 128) keeps 8 interleaved
+// accumulators r_c = a[c] + a[c+8] + ..., so lane c owns chain c (same additions, same order), the chains are combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) with xor-shuffles (IEEE addition is commutative, so both partners get identical
+// bits) and the tail elements are added last -- bit-identical to np.mean(loss * noise, axis=1) with 8x the parallelism.
+// mode 0: estimate + update, mode 3: estimate only (get_grad).
+__global__ void __launch_bounds__(256)
+nes_update8_kernel(FbNesDev st, int mode) {
+  if (st.flags[0]) return;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = gt >> 3;
+  const int c = (int)(gt & 7);
+  const bool valid = n < st.N;
+  const int64_t nn = valid ? n : st.N - 1;
+  const double *loss = st.red + st.N;
+  const int S = st.S, S2 = st.pairs_total;
+  ColGetter get{st.noise, loss, st.N, nn, S2};
+  const int full = S - (S % 8);
+  double r = get(c);
+  for (int i = 8 + c; i < full; i += 8) r = __dadd_rn(r, get(i));
+  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+  for (int i = full; i < S; ++i) r = __dadd_rn(r, get(i));
+  double dist = 0.0;
+  if (valid && c == 0) {
+    const double g = __ddiv_rn(__ddiv_rn(r, (double)S), st.sigma);
+    if (mode == 3) {
+      st.gest[n] = g;
+    } else {
+      const double lr = st.state_f64[0];
+      const double G = __dadd_rn(__dmul_rn(st.momentum, st.grad[n]), __dmul_rn(st.one_minus_momentum, g));
+      st.grad[n] = G;
+      const double sg = (G > 0.0) ? 1.0 : ((G < 0.0) ? -1.0 : G);      // np.sign (0 -> 0, nan -> nan)
+      double a = __dadd_rn(st.adver[n], -__dmul_rn(lr, sg));
+      a = fmin(fmax(a, st.lower[n]), st.upper[n]);
+      st.adver[n] = a;
+      dist = fabs(__dadd_rn(st.audio[n], -a));
+    }
+  }
+  if (mode == 3) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dist = fmax(dist, __shfl_xor_sync(0xffffffffu, dist, o));
   if ((threadIdx.x & 31) == 0 && dist > 0.0)
@@ -487,7 +559,10 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
   ctx->launches += 1;
   const int nb = fb_div_up(s->N, 128);
   if (!multi) {
-    nes_update_kernel<<<nb, 128, 0, ctx->stream>>>(d, mode_get_grad ? 3 : 0, 1, 0.0);
+    if (d.S >= 8 && d.S <= 128)
+      nes_update8_kernel<<<fb_div_up(s->N * 8, 256), 256, 0, ctx->stream>>>(d, mode_get_grad ? 3 : 0);
+    else
+      nes_update_kernel<<<nb, 128, 0, ctx->stream>>>(d, mode_get_grad ? 3 : 0, 1, 0.0);
     ctx->launches += 1;
   } else {
     nes_update_kernel<<<nb, 128, 0, ctx->stream>>>(d, 1, 1, 0.0);

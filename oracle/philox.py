@@ -8,13 +8,13 @@ bit-for-bit on the integer side so the oracle can replay it:
 
   key      = (seed_lo, seed_hi)
   counter  = (n // 4, pair_index j, iter_lo, iter_hi)          one call -> 4 x uint32
-  u_a      = (x_{2q}   + 0.5) * 2^-32 ,  u_b = (x_{2q+1} + 0.5) * 2^-32     q = 0, 1
-  z_{2q}   = sqrt(-2 ln u_a) * cos(2 pi u_b),  z_{2q+1} = sqrt(-2 ln u_a) * sin(2 pi u_b)
-  noise[n = 4*(n//4) + i, j] = z_i                                          (float64)
+  u_a      = ((x_{2q} >> 9) + 0.5) * 2^-23 ,  u_b = ((x_{2q+1} >> 9) + 0.5) * 2^-23     q = 0, 1   (exact in float32)
+  z_{2q}   = sqrt(-2 ln u_a) * cos(2 pi u_b),  z_{2q+1} = sqrt(-2 ln u_a) * sin(2 pi u_b)     (float32 arithmetic)
+  noise[n = 4*(n//4) + i, j] = float64(z_i)
 
-The integer stream is exact; ``log``/``sin``/``cos`` are evaluated by each side's libm
-in float64 (<= 2 ulp apart), which is far below the int16 quantisation step the
-perturbed audio goes through (``gmm_ubm_OSI.py:83-85``).
+The integer stream and the uniforms are exact; ``log``/``sin``/``cos`` are evaluated by each side's float32 libm
+(<= 2 ulp apart, i.e. ~1e-7 relative), far below the int16 quantisation step the perturbed audio goes through
+(``gmm_ubm_OSI.py:83-85``): a perturbed sample differs between the two sides with probability ~3e-6.
 """
 import numpy as np
 
@@ -51,12 +51,15 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-TWO_PI = 6.283185307179586
-INV_2_32 = 2.0 ** -32
+F32 = np.float32
+TWO_PI_F = F32(6.2831855)
+SCALE_23 = F32(2.0 ** -23)
 
 
 def normal_noise(seed, it, n_samples, n_pairs):
-    """-> (n_samples, n_pairs) float64, the device ``rng='philox'`` stream for iteration ``it``."""
+    """-> (n_samples, n_pairs) float64, the device ``rng='philox'`` stream for iteration ``it``.
+
+    Box-Muller in float32 on 23-bit uniforms u = ((x >> 9) + 0.5) * 2^-23 (exact), widened to float64."""
     seed = int(seed)
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     ng = (n_samples + 3) // 4
@@ -69,10 +72,10 @@ def normal_noise(seed, it, n_samples, n_pairs):
     x0, x1, x2, x3 = philox4x32_10(c0, c1, c2, c3, k0, k1)
     out = np.empty((ng, 4, n_pairs), dtype=np.float64)
     for q, (xa, xb) in enumerate(((x0, x1), (x2, x3))):
-        ua = (xa.astype(np.float64) + 0.5) * INV_2_32
-        ub = (xb.astype(np.float64) + 0.5) * INV_2_32
-        rad = np.sqrt(-2.0 * np.log(ua))
-        ang = TWO_PI * ub
-        out[:, 2 * q, :] = rad * np.cos(ang)
-        out[:, 2 * q + 1, :] = rad * np.sin(ang)
+        ua = (((xa >> np.uint32(9)).astype(F32) + F32(0.5)) * SCALE_23).astype(F32)
+        ub = (((xb >> np.uint32(9)).astype(F32) + F32(0.5)) * SCALE_23).astype(F32)
+        rad = np.sqrt((F32(-2.0) * np.log(ua)).astype(F32)).astype(F32)
+        ang = (TWO_PI_F * ub).astype(F32)
+        out[:, 2 * q, :] = (rad * np.cos(ang).astype(F32)).astype(F32)
+        out[:, 2 * q + 1, :] = (rad * np.sin(ang).astype(F32)).astype(F32)
     return out.reshape(ng * 4, n_pairs)[:n_samples]
