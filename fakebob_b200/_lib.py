@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfakebob_b200.so")
+LIB_PATH = os.environ.get("FB_LIB_PATH") or os.path.join(_HERE, "libfakebob_b200.so")   # override: kernel experiments only
 
 
 class FakebobLibraryError(RuntimeError):

@@ -31,7 +31,8 @@
 #ifndef GMM_PARTS
 #define GMM_PARTS 3
 #endif
-#define GMM_THREADS 320                       // producer warp + MMA warp + 8 epilogue warps
+#define GMM_THREADS 352                       // producer warp + MMA issuer (tile 0) + 8 epilogue warps + MMA issuer (tile 1)
+#define GMM_ISSUER1 10
 // Operand K layout (slabs of 8 fp16) for the hi and lo halves of A and W alike:
 //   [x 0..8][ones | gconst 9][x^2 10..18][zero 19]   (20 slabs = 10 k-blocks of K=16; each half is 5 k-blocks)
 // gconst*log2(e) sits in W's slab 9 as three fp16 terms (g_hi, g_mid, g_lo) against three 1.0 columns of A's "ones" slab,
@@ -210,6 +211,13 @@ __device__ __forceinline__ void lse_group(const float *v, float &m, float &s) {
 // registers, and every model only needs  T_m = x . (mu_m/var) + g_m  (15 MMAs instead of 30); the epilogue forms
 // ll_m = Q + T_m.  Every accumulator starts from zero, so the (truncating) tensor-core accumulation error is the same for
 // all models and cancels in log-likelihood-ratio scores.
+#ifdef GMM_STATS
+#define STAT_DECL(x) long long x = 0
+#define STAT_WAIT(acc, bar, par) do { const long long t_ = clock64(); mbar_wait(bar, par); acc += clock64() - t_; } while (0)
+#else
+#define STAT_DECL(x)
+#define STAT_WAIT(acc, bar, par) mbar_wait(bar, par)
+#endif
 template <bool kStore, bool kShared>
 __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   if (g.done_flag && *g.done_flag) return;
@@ -219,8 +227,11 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   uint8_t *smem = smem_raw + (base - raw_addr);
   const uint32_t bar0 = base + kSmemBar;
   const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kNumSlots;           // ring slots
-  const uint32_t bar_acc_full = bar0 + 16 * kNumSlots, bar_acc_empty = bar_acc_full + 8 * kNumAcc;   // [kNumAcc] each
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmemBar + 16 * kNumSlots + 16 * kNumAcc + 8);
+  // accumulator barriers are per (accumulator, tile): full[a][t] issuer t -> epilogue t, empty[a][t] epilogue t -> issuer 1-t
+  // (the next user of accumulator a).  One barrier per accumulator would be waited on by the two issuers / epilogue groups
+  // alternately, each skipping every other phase, which a parity wait cannot tell apart.
+  const uint32_t bar_acc_full = bar0 + 16 * kNumSlots, bar_acc_empty = bar_acc_full + 16 * kNumAcc;   // [kNumAcc][2] each
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmemBar + 16 * kNumSlots + 32 * kNumAcc + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.misc[2];
@@ -236,9 +247,9 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   if (warp == 0 && lane == 0) {
     for (uint32_t i = 0; i < kNumSlots; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 2);          // one arrive per issuer warp
     }
-    for (uint32_t i = 0; i < kNumAcc; ++i) {
+    for (uint32_t i = 0; i < 2 * kNumAcc; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
       mbar_init(bar_acc_empty + 8 * i, 4);     // one arrive per epilogue warp of the tile that read it
     }
@@ -258,6 +269,10 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     // ================= producer: ring of kNumSlots slots (whole warp loops, one elected lane issues) =================
     int cur_super = -1;
     uint32_t cnt = 0;
+    STAT_DECL(st_prod_empty);
+#ifdef GMM_STATS
+    const long long st_t0 = clock64();
+#endif
     for (int u = u0; u < u1; ++u) {
       const int ch = u % nch;
       const int item = u / nch;
@@ -268,7 +283,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
         for (int e = 0; e < 4; ++e) {          // tile0 hi, tile0 lo, tile1 hi, tile1 lo
           const uint32_t slot = cnt % kNumSlots;
-          mbar_wait(bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+          STAT_WAIT(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
           if (elect_one()) {
             mbar_expect_tx(bar_full + 8 * slot, kAHalfBytes);
             bulk_g2s(base + slot * kSlotBytes, src + (size_t)e * kAHalfBytes, kAHalfBytes, bar_full + 8 * slot);
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
         for (int q = 0; q < n_sub; q += kShared ? 2 : 1) {
           const uint32_t slot = cnt % kNumSlots;
-          mbar_wait(bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+          STAT_WAIT(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
           if (elect_one()) {
             const uint32_t bytes = kShared ? ((q + 1 < n_sub) ? 2 * kWShBytes : kWShBytes) : kWStageBytes;
             const size_t off = kShared ? (stage * n_sub + q) * (size_t)kWShBytes
@@ -299,13 +314,26 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== tcgen05 issuer (whole warp loops and waits; one elected lane issues copies / MMAs / commits) =====
+#ifdef GMM_STATS
+    if (lane == 0 && (blockIdx.x % 37) == 0)
+      printf("cta %3d producer: total %lld clk, waiting for empty slots %lld, units %d\n", blockIdx.x, clock64() - st_t0, st_prod_empty, u1 - u0);
+#endif
+  } else if (warp == 1 || warp == GMM_ISSUER1) {
+    // ===== tcgen05 issuers: warp 1 owns tile 0, warp GMM_ISSUER1 owns tile 1 (whole warp loops and waits; one elected lane
+    // issues copies / MMAs / commits).  Two issuers because the tensor pipe's issue queue is shallow (measured,
+    // scripts/mma_probe.cu: every mbarrier wait between two 15-MMA jobs of ONE thread idles the pipe ~130 clk, 480 -> 700+
+    // clk per job); while one issuer is in its wait / commit overhead the other one's MMAs keep the pipe busy.
+    // Both walk the same sequence of ring entries; a slot is released by two arrivals (one per issuer).
+    const int tile = (warp == 1) ? 0 : 1;
     // smem descriptor with LBO / SBO / version bits and a zero start address; only the 14-bit address field varies
     const uint64_t desc_w = make_desc(0, kSlabW, 128);
     const uint64_t desc_a = make_desc(0, kSlabA, 128);
     int cur_super = -1;
-    uint32_t cnt = 0, job = 0;                      // job = running (tile, sub-step) counter; accumulator = job % 3
+    uint32_t cnt = 0, job = tile;                   // job = global (sub-step, tile) counter = 2 * step + tile; accumulator = job % 3
+    STAT_DECL(st_mma_full); STAT_DECL(st_mma_acc); STAT_DECL(st_mma_afull);
+#ifdef GMM_STATS
+    const long long st_t0 = clock64();
+#endif
     for (int u = u0; u < u1; ++u) {
       const int item = u / nch;
       const int sp = item / models_per_unit;
@@ -313,14 +341,20 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
         for (int e = 0; e < 4; ++e) {
           const uint32_t slot = cnt % kNumSlots;
-          mbar_wait(bar_full + 8 * slot, (cnt / kNumSlots) & 1);
+          // the other tile's entries are waited for as well: "full" proves the slot's previous use was released, so the
+          // plain arrive below cannot land in the previous phase of the empty barrier
+          STAT_WAIT(st_mma_afull, bar_full + 8 * slot, (cnt / kNumSlots) & 1);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t src = desc_a + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
-            const uint32_t dst = tmem_base + kTmemA + (e >> 1) * kTmemATileCols + (e & 1) * kTmemAHalfCols;
+            if ((e >> 1) == tile) {
+              const uint64_t src = desc_a + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
+              const uint32_t dst = tmem_base + kTmemA + tile * kTmemATileCols + (e & 1) * kTmemAHalfCols;
 #pragma unroll
-            for (int kb = 0; kb < FB_A_HI_SLABS / 2; ++kb) tc_cp_128x256b(dst + kb * 8, src + (uint64_t)(kb * ((2 * kSlabA) >> 4)));
-            tc_commit(bar_empty + 8 * slot);
+              for (int kb = 0; kb < FB_A_HI_SLABS / 2; ++kb) tc_cp_128x256b(dst + kb * 8, src + (uint64_t)(kb * ((2 * kSlabA) >> 4)));
+              tc_commit(bar_empty + 8 * slot);
+            } else {
+              mbar_arrive(bar_empty + 8 * slot);
+            }
           }
           __syncwarp();
           ++cnt;
@@ -334,50 +368,74 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           const uint32_t slot = cnt % kNumSlots;
           const bool first_in_slot = !kShared || (q & 1) == 0;
           const bool last_in_slot = !kShared || (q & 1) == 1 || q + 1 == n_sub;
-          if (first_in_slot) mbar_wait(bar_full + 8 * slot, (cnt / kNumSlots) & 1);
+          if (first_in_slot) STAT_WAIT(st_mma_full, bar_full + 8 * slot, (cnt / kNumSlots) & 1);
           const uint32_t sub_off = (kShared && (q & 1)) ? kWShBytes : 0;
           const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes + sub_off) & 0x3FFFFu) >> 4);
           const uint64_t w_lo = w_hi + (uint64_t)((kShared ? kWShHalfBytes : kWHalfBytes) >> 4);
           // shared mode: q = 0 is the x^2 sub-step, q >= 1 the x (+ gconst) sub-step of model q-1; all start from zero
           const uint32_t a_off = (kShared && q == 0) ? kTmemX2Cols : 0;
+          const uint32_t abuf = job % kNumAcc;
+          // accumulator abuf was last used by job - 3, a job of the other tile: wait until that tile's epilogue has read it
+          if (job >= kNumAcc) STAT_WAIT(st_mma_acc, bar_acc_empty + 8 * (2 * abuf + (tile ^ 1)), ((job - kNumAcc) / (2 * kNumAcc)) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols + a_off;
+            const uint32_t a_lo = a_hi + kTmemAHalfCols;
+            const uint32_t d_tmem = tmem_base + kTmemAcc + abuf * FB_STAGE_N;
+            constexpr int nkb = kShared ? 5 : 10;
 #pragma unroll
-          for (int tile = 0; tile < 2; ++tile) {
-            const uint32_t abuf = job % kNumAcc;
-            mbar_wait(bar_acc_empty + 8 * abuf, ((job / kNumAcc) & 1) ^ 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols + a_off;
-              const uint32_t a_lo = a_hi + kTmemAHalfCols;
-              const uint32_t d_tmem = tmem_base + kTmemAcc + abuf * FB_STAGE_N;
-              constexpr int nkb = kShared ? 5 : 10;
+            for (int part = 0; part < GMM_PARTS; ++part) {
+              const uint32_t a_base = (part == 1) ? a_lo : a_hi;
+              const uint64_t b_base = (part == 2) ? w_lo : w_hi;
 #pragma unroll
-              for (int part = 0; part < GMM_PARTS; ++part) {
-                const uint32_t a_base = (part == 1) ? a_lo : a_hi;
-                const uint64_t b_base = (part == 2) ? w_lo : w_hi;
-#pragma unroll
-                for (int kb = 0; kb < nkb; ++kb) {
-                  tc_mma_f16_ta(d_tmem, a_base + kb * 8, b_base + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
-                }
+              for (int kb = 0; kb < nkb; ++kb) {
+                tc_mma_f16_ta(d_tmem, a_base + kb * 8, b_base + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
               }
-              tc_commit(bar_acc_full + 8 * abuf);
-              if (tile == 1 && last_in_slot) tc_commit(bar_empty + 8 * slot);
             }
-            __syncwarp();
-            ++job;
+            tc_commit(bar_acc_full + 8 * (2 * abuf + tile));
+            if (last_in_slot) tc_commit(bar_empty + 8 * slot);
           }
+          __syncwarp();
+          job += 2;
           if (last_in_slot) ++cnt;
         }
       }
     }
+#ifdef GMM_STATS
+    if (lane == 0 && (blockIdx.x % 37) == 0)
+      printf("cta %3d mma tile %d: total %lld clk, waiting W full %lld, A full %lld, acc empty %lld, jobs %u\n", blockIdx.x, tile, clock64() - st_t0, st_mma_full, st_mma_afull, st_mma_acc, job / 2);
+#endif
   } else {
     // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, tile = (warp - 2) / 4 =====
     const int quad = warp & 3;
     const int tile = (warp - 2) >> 2;
     uint32_t job = tile;                               // this tile's jobs are tile, tile + 2, tile + 4, ...
     const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc;
-    const int n_read = kShared ? g.n_models + 1 : 1;   // accumulator reads per 64-column stage (shared: Q, then each model)
-    float mm[kShared ? FB_MAX_MODELS + 1 : 1], ss[kShared ? FB_MAX_MODELS + 1 : 1];
+    float mm[kShared ? FB_MAX_MODELS : 1], ss[kShared ? FB_MAX_MODELS : 1];
     int run_item = -1;                                  // the running maxima belong to this (super[, model])
+    STAT_DECL(st_epi_full);
+#ifdef GMM_STATS
+    const long long st_t0 = clock64();
+#endif
+    // wait for this tile's next accumulator, pull its 64 columns of this warp's 32 lanes into registers, hand it back
+    auto fetch = [&](float (&va)[32], float (&vb)[32]) {
+      const uint32_t abuf = job % kNumAcc;
+      STAT_WAIT(st_epi_full, bar_acc_full + 8 * (2 * abuf + tile), (job / (2 * kNumAcc)) & 1);
+      tc_fence_after();
+      const uint32_t taddr = taddr0 + abuf * FB_STAGE_N;
+#ifndef GMM_NO_LDTM
+      tc_ld32(taddr, va);
+      tc_ld32(taddr + 32, vb);
+      tc_wait_ld();
+#else
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { va[i] = (float)(i + job); vb[i] = (float)(i - job); }
+#endif
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * (2 * abuf + tile));   // accumulator is in registers: the next job may overwrite
+      job += 2;
+    };
     for (int u = u0; u < u1; ++u) {
       const int ch = u % nch;
       const int item = u / nch;
@@ -386,42 +444,26 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
       // the running row maximum is kept across consecutive 128-column units of the same rows and model, so the cutoff is
       // (almost) relative to the global maximum; each unit still writes its own (max, sum) partial
-      for (int i = 0; i < n_read; ++i) {
+      const int n_run = kShared ? g.n_models : 1;
+      for (int i = 0; i < n_run; ++i) {
         if (item != run_item) mm[i] = -INFINITY;
         ss[i] = 0.f;
       }
       run_item = item;
-      float qa[kShared ? 32 : 1], qb[kShared ? 32 : 1];   // shared mode: the x^2 term of this stage
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
+        if constexpr (kShared) {
+          float qa[32], qb[32];                         // the x^2 term Q of this (rows, 64-column stage)
+          fetch(qa, qb);
 #pragma unroll 1
-        for (int r = 0; r < n_read; ++r) {
-          const uint32_t abuf = job % kNumAcc;
-          mbar_wait(bar_acc_full + 8 * abuf, (job / kNumAcc) & 1);
-          tc_fence_after();
-          float va[32], vb[32];
-          const uint32_t taddr = taddr0 + abuf * FB_STAGE_N;
-          tc_ld32(taddr, va);
-          tc_ld32(taddr + 32, vb);
-          tc_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * abuf);     // accumulator is in registers: MMA may overwrite
-          job += 2;
-          if (kStore) {
-            float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + ch * FB_CHUNK_N + h * FB_STAGE_N);
-            const float ln2 = 0.6931471805599453f;
+          for (int r = 0; r < g.n_models; ++r) {
+            float va[32], vb[32];
+            fetch(va, vb);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(va[i] * ln2, va[i + 1] * ln2, va[i + 2] * ln2, va[i + 3] * ln2);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) dst[8 + (i >> 2)] = make_float4(vb[i] * ln2, vb[i + 1] * ln2, vb[i + 2] * ln2, vb[i + 3] * ln2);
-          } else if (kShared && r == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { qa[i] = va[i]; qb[i] = vb[i]; }
-          } else {
-            if (kShared) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) { va[i] += qa[i]; vb[i] += qb[i]; }
+            for (int i = 0; i < 32; i += 2) {
+              const float2 t0 = __fadd2_rn(make_float2(va[i], va[i + 1]), make_float2(qa[i], qa[i + 1]));
+              const float2 t1 = __fadd2_rn(make_float2(vb[i], vb[i + 1]), make_float2(qb[i], qb[i + 1]));
+              va[i] = t0.x; va[i + 1] = t0.y; vb[i] = t1.x; vb[i + 1] = t1.y;
             }
             float m = mm[r], sacc = ss[r];
 #ifndef GMM_NO_LSE
@@ -433,15 +475,40 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
             mm[r] = m;
             ss[r] = sacc;
           }
+        } else {
+          float va[32], vb[32];
+          fetch(va, vb);
+          if constexpr (kStore) {
+            float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + ch * FB_CHUNK_N + h * FB_STAGE_N);
+            const float ln2 = 0.6931471805599453f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(va[i] * ln2, va[i + 1] * ln2, va[i + 2] * ln2, va[i + 3] * ln2);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) dst[8 + (i >> 2)] = make_float4(vb[i] * ln2, vb[i + 1] * ln2, vb[i + 2] * ln2, vb[i + 3] * ln2);
+          } else {
+            float m = mm[0], sacc = ss[0];
+#ifndef GMM_NO_LSE
+            lse_group(va, m, sacc);
+            lse_group(vb, m, sacc);
+#else
+            m = fmaxf(m, va[0] + vb[31]);
+#endif
+            mm[0] = m;
+            ss[0] = sacc;
+          }
         }
       }
-      if (!kStore) {
-        for (int r = kShared ? 1 : 0; r < n_read; ++r) {
-          const int mdl = kShared ? r - 1 : model;
+      if constexpr (!kStore) {
+        for (int r = 0; r < n_run; ++r) {
+          const int mdl = kShared ? r : model;
           g.part[((size_t)mdl * nch + ch) * g.rows_cap + row] = make_float2(mm[r], ss[r]);
         }
       }
     }
+#ifdef GMM_STATS
+    if (lane == 0 && (blockIdx.x % 37) == 0 && (warp == 2 || warp == 6))
+      printf("cta %3d epilogue warp %d: total %lld clk, waiting acc full %lld\n", blockIdx.x, warp, clock64() - st_t0, st_epi_full);
+#endif
   }
   tc_fence_before();
   __syncthreads();
