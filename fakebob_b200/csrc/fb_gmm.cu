@@ -166,37 +166,42 @@ static constexpr uint32_t kIdesc = (1u << 4) | ((FB_STAGE_N >> 3) << 17) | ((FB_
 struct GmmArgs {
   const __half *a_img;      // [tile][hi 19 slabs | lo 18 slabs][128][8]
   const __half *w_img;      // [model][C/64][hi 20 slabs | lo 18 slabs][64][8]
-  float2 *part;             // [model][C/128][rows_cap]
+  float2 *part;             // [model][C/64][rows_cap]: (max, sum) of the segment of 64-column stages that STARTS at that stage
   const int *misc;          // misc[2] = total voiced rows
   const int *done_flag;
   float *ll_out;            // STORE mode: [rows_cap][C] natural-log component log-likelihoods (Gaussian selection)
   int n_models, C, rows_cap;
 };
 
-// One 32-column batch of one accumulator row: online max / sum of 2^(v - max) with Kaldi's cutoff (LogSumExp drops terms
-// below max + log(FLT_EPSILON) = max - 23 in log2).  Only ~0.5 % of the terms survive that cutoff, so the exponentials are
+// 64 accumulator columns of one row: online max / sum of 2^(v - max) with Kaldi's cutoff (LogSumExp drops terms below
+// max + log(FLT_EPSILON) = max - 23 in log2).  Only ~0.5 % of the terms survive that cutoff, so the exponentials are
 // evaluated per 8-column group and only when a warp vote finds a lane that still needs them (measured on the C2 model:
-// ~75 % of the warp x 8-column groups are dead).  `m` is the running row maximum, `s` the sum relative to it.
-__device__ __forceinline__ void lse_group(const float *v, float &m, float &s) {
-  float gmax[4];
+// ~75 % of the warp x 8-column groups are dead).  All eight votes are taken before the first exponential so their
+// latencies overlap.  `m` is the running row maximum, `s` the sum relative to it.
+__device__ __forceinline__ void lse_stage(const float *va, const float *vb, float &m, float &s) {
+  float gmax[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float *q = v + 8 * k;
+  for (int k = 0; k < 8; ++k) {
+    const float *q = (k < 4) ? va + 8 * k : vb + 8 * (k - 4);
     gmax[k] = max3(max3(q[0], q[1], q[2]), max3(q[3], q[4], q[5]), fmaxf(q[6], q[7]));
   }
-  const float cmax = max3(gmax[0], gmax[1], fmaxf(gmax[2], gmax[3]));
+  const float cmax = fmaxf(max3(gmax[0], gmax[1], gmax[2]), max3(gmax[3], gmax[4], max3(gmax[5], gmax[6], gmax[7])));
   if (cmax > m) {
     s *= ex2_approx(m - cmax);
     m = cmax;
   }
   const float thr = m - 23.0f;
+  bool alive[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (__any_sync(0xffffffffu, gmax[k] >= thr)) {
+  for (int k = 0; k < 8; ++k) alive[k] = __any_sync(0xffffffffu, gmax[k] >= thr);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (alive[k]) {
+      const float *q = (k < 4) ? va + 8 * k : vb + 8 * (k - 4);
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
-        const float t0 = v[8 * k + i] - m, t1 = v[8 * k + i + 1] - m;
+        const float t0 = q[i] - m, t1 = q[i + 1] - m;
         const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
         if (t0 >= -23.0f) s0 += e0;
         if (t1 >= -23.0f) s1 += e1;
@@ -212,6 +217,12 @@ __device__ __forceinline__ void lse_group(const float *v, float &m, float &s) {
 // ll_m = Q + T_m.  Every accumulator starts from zero, so the (truncating) tensor-core accumulation error is the same for
 // all models and cancels in log-likelihood-ratio scores.
 #ifdef GMM_STATS
+// [cta][16]: 0 entry globaltimer, 1 exit-entry ns, 2 setup clk, 3 total clk, 4 producer total, 5 producer wait empty,
+// 6/7 issuer0 total / waits, 8/9 issuer1 total / waits, 10/11 epilogue warp 2 total / wait full, 12/13 epilogue warp 6
+__device__ long long g_gmm_stats[148 * 16];
+extern "C" int fb_debug_gmm_stats(long long *out_host) {
+  return cudaMemcpyFromSymbol(out_host, g_gmm_stats, sizeof(g_gmm_stats)) == cudaSuccess ? 0 : -1;
+}
 #define STAT_DECL(x) long long x = 0
 #define STAT_WAIT(acc, bar, par) do { const long long t_ = clock64(); mbar_wait(bar, par); acc += clock64() - t_; } while (0)
 #else
@@ -220,6 +231,11 @@ __device__ __forceinline__ void lse_group(const float *v, float &m, float &s) {
 #endif
 template <bool kStore, bool kShared>
 __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
+#ifdef GMM_STATS
+  unsigned long long gt_entry;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
+  const long long ck_entry = clock64();
+#endif
   if (g.done_flag && *g.done_flag) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -235,11 +251,13 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.misc[2];
-  const int nch = g.C / FB_CHUNK_N;
+  const int nst = g.C / FB_STAGE_N;
   const int n_super = (M + 2 * FB_TILE_M - 1) / (2 * FB_TILE_M);
-  // general: unit = (super, model, chunk); shared: unit = (super, chunk), all models inside
+  // Work = the sequence of 64-column stages ordered (super-tile, [model,] stage); general mode: one model per stage,
+  // shared mode: all models inside a stage.  CTA b takes the contiguous range [total b / grid, total (b+1) / grid)
+  // (gmm_frame_kernel recomputes these boundaries to find the partials of a row).
   const int models_per_unit = kShared ? 1 : g.n_models;
-  const long long n_units = (long long)n_super * models_per_unit * nch;
+  const long long n_units = (long long)n_super * models_per_unit * nst;
   const int u0 = (int)(n_units * blockIdx.x / gridDim.x);
   const int u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
   const int n_sub = kShared ? g.n_models + 1 : 1;                              // ring entries per 64-column stage
@@ -264,6 +282,9 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef GMM_STATS
+  const long long ck_setup = clock64();
+#endif
 
   if (warp == 0) {
     // ================= producer: ring of kNumSlots slots (whole warp loops, one elected lane issues) =================
@@ -274,8 +295,8 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     const long long st_t0 = clock64();
 #endif
     for (int u = u0; u < u1; ++u) {
-      const int ch = u % nch;
-      const int item = u / nch;
+      const size_t stage = u % nst;
+      const int item = u / nst;
       const int model = item % models_per_unit;
       const int sp = item / models_per_unit;
       if (sp != cur_super) {
@@ -293,9 +314,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         }
         cur_super = sp;
       }
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const size_t stage = (size_t)ch * 2 + h;
+      {
         // a bulk copy costs ~930 clk whatever its size (<= 40 KB) and copies of one SM do not overlap, so the shared
         // mode fetches its 20 KB sub-stages two per ring entry
 #pragma unroll 1
@@ -315,8 +334,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       }
     }
 #ifdef GMM_STATS
-    if (lane == 0 && (blockIdx.x % 37) == 0)
-      printf("cta %3d producer: total %lld clk, waiting for empty slots %lld, units %d\n", blockIdx.x, clock64() - st_t0, st_prod_empty, u1 - u0);
+    if (lane == 0) { g_gmm_stats[blockIdx.x * 16 + 4] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 5] = st_prod_empty; }
 #endif
   } else if (warp == 1 || warp == GMM_ISSUER1) {
     // ===== tcgen05 issuers: warp 1 owns tile 0, warp GMM_ISSUER1 owns tile 1 (whole warp loops and waits; one elected lane
@@ -335,7 +353,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     const long long st_t0 = clock64();
 #endif
     for (int u = u0; u < u1; ++u) {
-      const int item = u / nch;
+      const int item = u / nst;
       const int sp = item / models_per_unit;
       if (sp != cur_super) {
 #pragma unroll 1
@@ -361,8 +379,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         }
         cur_super = sp;
       }
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
+      {
 #pragma unroll 1
         for (int q = 0; q < n_sub; ++q) {
           const uint32_t slot = cnt % kNumSlots;
@@ -402,8 +419,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       }
     }
 #ifdef GMM_STATS
-    if (lane == 0 && (blockIdx.x % 37) == 0)
-      printf("cta %3d mma tile %d: total %lld clk, waiting W full %lld, A full %lld, acc empty %lld, jobs %u\n", blockIdx.x, tile, clock64() - st_t0, st_mma_full, st_mma_afull, st_mma_acc, job / 2);
+    if (lane == 0) { g_gmm_stats[blockIdx.x * 16 + 6 + 2 * tile] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 7 + 2 * tile] = st_mma_full + st_mma_afull + st_mma_acc; }
 #endif
   } else {
     // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, tile = (warp - 2) / 4 =====
@@ -436,22 +452,32 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * (2 * abuf + tile));   // accumulator is in registers: the next job may overwrite
       job += 2;
     };
+    // The running (max, sum) of a row is kept over the whole run of consecutive stages this CTA computes for the same
+    // (rows[, model]) -- a "segment" -- so the cutoff is relative to the running maximum; one partial per segment, stored
+    // at the index of the segment's first stage.
+    const int n_run = kShared ? g.n_models : 1;
+    int seg_start = 0, seg_row = 0, seg_model = 0;
+    auto flush = [&]() {
+      if constexpr (!kStore) {
+        for (int r = 0; r < n_run; ++r) {
+          const int mdl = kShared ? r : seg_model;
+          g.part[((size_t)mdl * nst + seg_start) * g.rows_cap + seg_row] = make_float2(mm[r], ss[r]);
+        }
+      }
+    };
     for (int u = u0; u < u1; ++u) {
-      const int ch = u % nch;
-      const int item = u / nch;
+      const int stage = u % nst;
+      const int item = u / nst;
       const int model = item % models_per_unit;
       const int sp = item / models_per_unit;
       const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
-      // the running row maximum is kept across consecutive 128-column units of the same rows and model, so the cutoff is
-      // (almost) relative to the global maximum; each unit still writes its own (max, sum) partial
-      const int n_run = kShared ? g.n_models : 1;
-      for (int i = 0; i < n_run; ++i) {
-        if (item != run_item) mm[i] = -INFINITY;
-        ss[i] = 0.f;
+      if (item != run_item) {
+        if (run_item >= 0) flush();
+        for (int i = 0; i < n_run; ++i) { mm[i] = -INFINITY; ss[i] = 0.f; }
+        run_item = item;
+        seg_start = stage; seg_row = row; seg_model = model;
       }
-      run_item = item;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
+      {
         if constexpr (kShared) {
           float qa[32], qb[32];                         // the x^2 term Q of this (rows, 64-column stage)
           fetch(qa, qb);
@@ -467,8 +493,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
             }
             float m = mm[r], sacc = ss[r];
 #ifndef GMM_NO_LSE
-            lse_group(va, m, sacc);
-            lse_group(vb, m, sacc);
+            lse_stage(va, vb, m, sacc);
 #else
             m = fmaxf(m, va[0] + vb[31]);
 #endif
@@ -479,7 +504,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           float va[32], vb[32];
           fetch(va, vb);
           if constexpr (kStore) {
-            float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + ch * FB_CHUNK_N + h * FB_STAGE_N);
+            float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + stage * FB_STAGE_N);
             const float ln2 = 0.6931471805599453f;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(va[i] * ln2, va[i + 1] * ln2, va[i + 2] * ln2, va[i + 3] * ln2);
@@ -488,8 +513,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           } else {
             float m = mm[0], sacc = ss[0];
 #ifndef GMM_NO_LSE
-            lse_group(va, m, sacc);
-            lse_group(vb, m, sacc);
+            lse_stage(va, vb, m, sacc);
 #else
             m = fmaxf(m, va[0] + vb[31]);
 #endif
@@ -498,20 +522,22 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           }
         }
       }
-      if constexpr (!kStore) {
-        for (int r = 0; r < n_run; ++r) {
-          const int mdl = kShared ? r : model;
-          g.part[((size_t)mdl * nch + ch) * g.rows_cap + row] = make_float2(mm[r], ss[r]);
-        }
-      }
     }
+    if (run_item >= 0) flush();
 #ifdef GMM_STATS
-    if (lane == 0 && (blockIdx.x % 37) == 0 && (warp == 2 || warp == 6))
-      printf("cta %3d epilogue warp %d: total %lld clk, waiting acc full %lld\n", blockIdx.x, warp, clock64() - st_t0, st_epi_full);
+    if (lane == 0 && (warp == 2 || warp == 6)) { g_gmm_stats[blockIdx.x * 16 + 10 + (warp == 6 ? 2 : 0)] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 11 + (warp == 6 ? 2 : 0)] = st_epi_full; }
 #endif
   }
   tc_fence_before();
   __syncthreads();
+#ifdef GMM_STATS
+  if (threadIdx.x == 0) {
+    unsigned long long gt_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_exit));
+    g_gmm_stats[blockIdx.x * 16 + 0] = (long long)gt_entry; g_gmm_stats[blockIdx.x * 16 + 1] = (long long)(gt_exit - gt_entry);
+    g_gmm_stats[blockIdx.x * 16 + 2] = ck_setup - ck_entry; g_gmm_stats[blockIdx.x * 16 + 3] = clock64() - ck_entry;
+  }
+#endif
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -565,7 +591,7 @@ gmm_simt_kernel(const __half *__restrict__ a_img, const float *__restrict__ w_f3
       const float t = s_ll[r][k] - m;
       if (t >= -23.0f) s += exp2f(t);
     }
-    part[((size_t)model * nch + ch) * rows_cap + row0 + r] = make_float2(m, s);
+    part[((size_t)model * (2 * nch) + 2 * ch) * rows_cap + row0 + r] = make_float2(m, s);   // stage index of the chunk's first stage
   }
 }
 
@@ -575,24 +601,39 @@ gmm_simt_kernel(const __half *__restrict__ a_img, const float *__restrict__ w_f3
 // Fixed reduction order (deterministic).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, float *__restrict__ frame_ll, int nch,
-                 int rows_cap, const int *__restrict__ done_flag) {
+gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, float *__restrict__ frame_ll, int nst,
+                 int rows_cap, const int *__restrict__ done_flag, int umma_grid, int models_per_unit) {
   if (done_flag && *done_flag) return;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const int model = blockIdx.y;
-  if (row >= misc[2]) return;
-  float2 p[32];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < 32; ++k)
-    if (k < nch) {
-      p[k] = part[((size_t)model * nch + k) * rows_cap + row];
-      mx = fmaxf(mx, p[k].x);
+  const int M = misc[2];
+  if (row >= M) return;
+  // The partials of this row are the segments gmm_umma_kernel cut its stage sequence into: recompute the CTA boundaries
+  // floor(total * b / grid) that fall inside this (super-tile[, model]) item.  umma_grid == 0: the fp32 cross-check kernel,
+  // one partial per 128-column chunk.
+  float2 p[64];                                  // C <= 4096: at most 64 stages, hence at most 64 segments
+  int n = 0;
+  if (umma_grid > 0) {
+    const int n_super = (M + 2 * FB_TILE_M - 1) / (2 * FB_TILE_M);
+    const long long total = (long long)n_super * models_per_unit * nst;
+    const int sp = row / (2 * FB_TILE_M);
+    const long long g0 = ((long long)sp * models_per_unit + (models_per_unit > 1 ? model : 0)) * nst;
+    long long st = g0;
+    while (st < g0 + nst) {
+      const long long b = ((st + 1) * umma_grid - 1) / total;                 // the CTA whose range contains stage st
+      long long end = total * (b + 1) / umma_grid;
+      if (end > g0 + nst) end = g0 + nst;
+      p[n++] = part[((size_t)model * nst + (int)(st - g0)) * rows_cap + row];
+      st = end;
     }
+  } else {
+    for (int k = 0; k < nst; k += 2) p[n++] = part[((size_t)model * nst + k) * rows_cap + row];
+  }
+  float mx = -INFINITY;
+  for (int k = 0; k < n; ++k) mx = fmaxf(mx, p[k].x);
   double s = 0.0;
-#pragma unroll
-  for (int k = 0; k < 32; ++k)
-    if (k < nch && p[k].x >= mx - 23.0f) s += (double)(p[k].y * exp2f(p[k].x - mx));
+  for (int k = 0; k < n; ++k)
+    if (p[k].x >= mx - 23.0f) s += (double)(p[k].y * exp2f(p[k].x - mx));
   frame_ll[(size_t)model * rows_cap + row] = (float)(((double)mx + log2(s)) * 0.6931471805599453);
 }
 
@@ -779,7 +820,8 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
 
 int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
   FB_CHECK_ARG(ctx->n_models > 0, "no GMMs loaded (fb_finalize_gmms)");
-  const int nch = ctx->C / FB_CHUNK_N;
+  const int nch = ctx->C / FB_CHUNK_N, nst = ctx->C / FB_STAGE_N;
+  int umma_grid = 0;
   if (ctx->gmm_impl == 0) {
     GmmArgs a;
     a.a_img = ctx->a_img.p;
@@ -791,9 +833,10 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     a.C = ctx->C;
     a.rows_cap = ctx->rows_cap;
     // upper bound on useful CTAs: one unit each
-    const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * (ctx->gmm_shared ? 1 : ctx->n_models) * nch;
+    const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * (ctx->gmm_shared ? 1 : ctx->n_models) * nst;
     int grid = ctx->num_sms;
     if (max_units < grid) grid = (int)max_units;
+    umma_grid = grid;
     a.ll_out = nullptr;
     if (ctx->gmm_shared) gmm_umma_kernel<false, true><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
     else gmm_umma_kernel<false, false><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
@@ -805,7 +848,7 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
   }
   fb_prof_mark(ctx, 4);
   gmm_frame_kernel<<<dim3(fb_div_up(ctx->total_frames, 128), ctx->n_models), 128, 0, ctx->stream>>>(
-      ctx->part.p, ctx->misc.p, ctx->frame_ll.p, nch, ctx->rows_cap, done_flag);
+      ctx->part.p, ctx->misc.p, ctx->frame_ll.p, nst, ctx->rows_cap, done_flag, umma_grid, ctx->gmm_shared ? 1 : ctx->n_models);
   gmm_reduce_kernel<<<dim3(ctx->B, ctx->n_models), 128, 0, ctx->stream>>>(ctx->frame_ll.p, ctx->row_off.p, ctx->avg_ll.p,
                                                                          ctx->n_models, ctx->rows_cap, done_flag);
   fb_prof_mark(ctx, 5);
@@ -819,7 +862,6 @@ int fb_run_gmm(fb_ctx *ctx) { return fb_run_gmm_flag(ctx, nullptr); }
 // Gaussian-selection pass of the i-vector path: slot 0 only, raw component log-likelihoods to ll_out [rows_cap][C].
 int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag) {
   FB_CHECK_ARG(ctx->n_models >= 1, "no GMMs loaded");
-  const int nch = ctx->C / FB_CHUNK_N;
   GmmArgs a;
   a.a_img = ctx->a_img.p;
   a.w_img = ctx->w_img.p;
@@ -830,7 +872,7 @@ int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag) {
   a.n_models = 1;
   a.C = ctx->C;
   a.rows_cap = ctx->rows_cap;
-  const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * nch;
+  const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * (ctx->C / FB_STAGE_N);
   int grid = ctx->num_sms;
   if (max_units < grid) grid = (int)max_units;
   FB_CHECK_ARG(!ctx->gmm_shared, "Gaussian selection needs the general W image");
