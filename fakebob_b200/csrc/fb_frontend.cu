@@ -593,7 +593,7 @@ int fb_reserve_batch(fb_ctx *ctx, int B, const int64_t *offsets_host) {
   }
   if (ctx->n_models > 0) {
     const size_t nst = ctx->C / FB_STAGE_N;          // one partial slot per 64-column stage (gmm_umma_kernel segments)
-    if ((rc = ctx->part.ensure((size_t)ctx->n_models * nst * 2 * ctx->rows_cap))) return rc;
+    if ((rc = ctx->part.ensure((size_t)ctx->n_models * nst * ctx->rows_cap))) return rc;
     if ((rc = ctx->frame_ll.ensure((size_t)ctx->n_models * ctx->rows_cap))) return rc;
     if ((rc = ctx->avg_ll.ensure((size_t)B * ctx->n_models))) return rc;
   }

@@ -11,29 +11,40 @@
 // which keeps ~22 significant bits per operand (fp32 Kaldi keeps 24).  W is pre-multiplied by
 // log2(e) so the epilogue works in the log2 domain with ex2.approx.
 //
-// Kernel shape (cta_group::1, persistent, 1 CTA / SM, 320 threads).  Measured on B200 (profiles/r01_*): with both
-// operands in shared memory the N=64 MMAs need 192 B/clk of smem reads and run at ~68 clk instead of 32, and they starve
-// the bulk-copy writes, so the A operand lives in TENSOR MEMORY instead:
+// Kernel shape (cta_group::1, persistent, 1 CTA / SM, 352 threads).  Measured on B200 (profiles/r01_*, scripts/*_probe.cu):
+//  * with both operands in shared memory the N=64 MMAs need 192 B/clk of smem reads and run at 48-68 clk instead of 32,
+//    so the A operand lives in TENSOR MEMORY;
+//  * the tensor pipe's issue queue is shallow: every mbarrier wait one thread does between two 15-MMA jobs idles the
+//    pipe ~130 clk (480 -> 700+ clk per job), while two issuing warps feeding different accumulators reach exactly
+//    32 clk/MMA whatever they wait for -> TWO issuer warps, one per 128-row tile;
+//  * tcgen05.ld moves 190-310 B/clk/SM and does not slow the MMAs down; a bulk copy of <= 40 KB takes ~970 clk.
 //   warp 0   bulk-copy (TMA engine, cp.async.bulk) producer into a 5-slot x 40 KB ring: per 256-row super-tile four
-//            A entries (tile0 hi, tile0 lo, tile1 hi, tile1 lo), then per 128-column unit two W stages (64 columns,
-//            hi+lo).  Operand images are stored in global memory already in the UMMA canonical no-swizzle K-major
-//            core-matrix order, so every copy is one contiguous transfer.
-//   warp 1   single thread: tcgen05.cp moves A entries smem -> TMEM (304 columns: 2 tiles x (hi 80 + lo 72)), then per W
-//            stage and tile 28 tcgen05.mma M128 N64 K16 with A from TMEM and B from the ring slot; the two tiles'
-//            accumulators (64 TMEM columns each) ping-pong against the epilogue.
-//   warps 2-9 epilogue (4 per tile, TMEM lane quadrant = warp % 4): tcgen05.ld 32x32b.x32, online max / sum of ex2 with
-//            Kaldi's log(FLT_EPSILON) pruning; gconst is already inside the accumulator (extra k-block of the hi.hi
-//            part: "ones" columns of A times [g_hi g_mid g_lo] rows of W); one (max,sum) partial per row per unit.
-// Work unit = (super-tile, model, 128-column chunk); units are split evenly over the CTAs.
+//            A entries (tile0 hi, tile0 lo, tile1 hi, tile1 lo), then the W stages (general: one 40 KB stage of 64
+//            columns, hi+lo; shared-variance mode: 20 KB sub-stages, two per ring entry).  Operand images are stored in
+//            global memory already in the UMMA canonical no-swizzle K-major core-matrix order, so every copy is one
+//            contiguous transfer.
+//   warp 1, warp 10   issuers (one elected lane each) for tile 0 / tile 1: tcgen05.cp moves their tile's A entries
+//            smem -> TMEM (304 columns: 2 tiles x (hi 80 + lo 72)), then per job 15 (shared mode) or 30 tcgen05.mma
+//            M128 N64 K16 with A from TMEM and B from the ring slot.  Jobs are numbered globally (2 * step + tile) and use
+//            accumulator job % 3 (three 64-column accumulators); a ring slot is released by one arrival per issuer.
+//            Barriers between issuers and epilogue are per (accumulator, tile) so that every barrier has one waiter that
+//            sees all of its phases (a parity wait cannot tell phase n from n+2).
+//   warps 2-9 epilogue (4 per tile, TMEM lane quadrant = warp % 4): tcgen05.ld 32x32b.x32, packed FADD2 of the shared x^2
+//            term, online max / sum of ex2 with Kaldi's log(FLT_EPSILON) pruning; gconst is already inside the accumulator
+//            (extra k-block of the hi.hi part: "ones" columns of A times [g_hi g_mid g_lo] rows of W).
+// Work = the sequence of 64-column stages ordered (super-tile, [model,] stage), cut into 148 equal contiguous ranges; a CTA
+// writes one (max, sum) partial per row and segment (run of its stages inside one super-tile), gmm_frame_kernel recomputes
+// the cut points to merge them.
+// Tried and rejected (same-clock A/B, cycles per CTA): 16 epilogue warps of 32 columns (+5 %); four accumulators (two per
+// tile, no cross-tile coupling) with the x^2-lo operand kept in shared memory and a 4-slot ring (+7 %).
 #include "fb_common.cuh"
 #include <math.h>
 
 #ifndef GMM_PARTS
 #define GMM_PARTS 3
 #endif
-#define GMM_THREADS 608                       // producer warp + 2 MMA issuer warps (tile 0, tile 1) + 16 epilogue warps
-#define GMM_ISSUER1 2
-#define GMM_EPI_WARP0 3
+#define GMM_THREADS 352                       // producer warp + MMA issuer (tile 0) + 8 epilogue warps + MMA issuer (tile 1)
+#define GMM_ISSUER1 10
 // Operand K layout (slabs of 8 fp16) for the hi and lo halves of A and W alike:
 //   [x 0..8][ones | gconst 9][x^2 10..18][zero 19]   (20 slabs = 10 k-blocks of K=16; each half is 5 k-blocks)
 // gconst*log2(e) sits in W's slab 9 as three fp16 terms (g_hi, g_mid, g_lo) against three 1.0 columns of A's "ones" slab,
@@ -167,38 +178,38 @@ static constexpr uint32_t kIdesc = (1u << 4) | ((FB_STAGE_N >> 3) << 17) | ((FB_
 struct GmmArgs {
   const __half *a_img;      // [tile][hi 19 slabs | lo 18 slabs][128][8]
   const __half *w_img;      // [model][C/64][hi 20 slabs | lo 18 slabs][64][8]
-  float2 *part;             // [model][C/64][2 column halves][rows_cap]: (max, sum) of the segment of 64-column stages that STARTS at that stage
+  float2 *part;             // [model][C/64][rows_cap]: (max, sum) of the segment of 64-column stages that STARTS at that stage
   const int *misc;          // misc[2] = total voiced rows
   const int *done_flag;
   float *ll_out;            // STORE mode: [rows_cap][C] natural-log component log-likelihoods (Gaussian selection)
   int n_models, C, rows_cap;
 };
 
-// 32 accumulator columns of one row: online max / sum of 2^(v - max) with Kaldi's cutoff (LogSumExp drops terms below
+// 64 accumulator columns of one row: online max / sum of 2^(v - max) with Kaldi's cutoff (LogSumExp drops terms below
 // max + log(FLT_EPSILON) = max - 23 in log2).  Only ~0.5 % of the terms survive that cutoff, so the exponentials are
 // evaluated per 8-column group and only when a warp vote finds a lane that still needs them (measured on the C2 model:
-// ~75 % of the warp x 8-column groups are dead).  All votes are taken before the first exponential so their latencies
-// overlap.  `m` is the running row maximum, `s` the sum relative to it.
-__device__ __forceinline__ void lse_stage(const float *v, float &m, float &s) {
-  float gmax[4];
+// ~75 % of the warp x 8-column groups are dead).  All eight votes are taken before the first exponential so their
+// latencies overlap.  `m` is the running row maximum, `s` the sum relative to it.
+__device__ __forceinline__ void lse_stage(const float *va, const float *vb, float &m, float &s) {
+  float gmax[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float *q = v + 8 * k;
+  for (int k = 0; k < 8; ++k) {
+    const float *q = (k < 4) ? va + 8 * k : vb + 8 * (k - 4);
     gmax[k] = max3(max3(q[0], q[1], q[2]), max3(q[3], q[4], q[5]), fmaxf(q[6], q[7]));
   }
-  const float cmax = max3(gmax[0], gmax[1], fmaxf(gmax[2], gmax[3]));
+  const float cmax = fmaxf(max3(gmax[0], gmax[1], gmax[2]), max3(gmax[3], gmax[4], max3(gmax[5], gmax[6], gmax[7])));
   if (cmax > m) {
     s *= ex2_approx(m - cmax);
     m = cmax;
   }
   const float thr = m - 23.0f;
-  bool alive[4];
+  bool alive[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) alive[k] = __any_sync(0xffffffffu, gmax[k] >= thr);
+  for (int k = 0; k < 8; ++k) alive[k] = __any_sync(0xffffffffu, gmax[k] >= thr);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 8; ++k) {
     if (alive[k]) {
-      const float *q = v + 8 * k;
+      const float *q = (k < 4) ? va + 8 * k : vb + 8 * (k - 4);
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     }
     for (uint32_t i = 0; i < 2 * kNumAcc; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 8);     // one arrive per epilogue warp of the tile that read it
+      mbar_init(bar_acc_empty + 8 * i, 4);     // one arrive per epilogue warp of the tile that read it
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -423,32 +434,30 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     if (lane == 0) { g_gmm_stats[blockIdx.x * 16 + 6 + 2 * tile] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 7 + 2 * tile] = st_mma_full + st_mma_afull + st_mma_acc; }
 #endif
   } else {
-    // ===== epilogue: warps 3..18; TMEM lane quadrant = warp % 4; (warp - 3) / 4 = 2 * half + tile: each accumulator is read
-    // by 8 warps (4 lane quadrants x 2 halves of 32 columns).  Sixteen warps because the per-job work is a dependent chain
-    // (tcgen05.ld -> add -> max tree -> votes -> exponentials): with 8 warps the epilogue took ~830 clk per job and tile
-    // against 960 clk of tensor-pipe time; more warps per scheduler hide that latency.
+    // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, tile = (warp - 2) / 4 =====
     const int quad = warp & 3;
-    const int tile = ((warp - GMM_EPI_WARP0) >> 2) & 1;
-    const int half = (warp - GMM_EPI_WARP0) >> 3;
+    const int tile = (warp - 2) >> 2;
     uint32_t job = tile;                               // this tile's jobs are tile, tile + 2, tile + 4, ...
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc + half * 32;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc;
     float mm[kShared ? FB_MAX_MODELS : 1], ss[kShared ? FB_MAX_MODELS : 1];
     int run_item = -1;                                  // the running maxima belong to this (super[, model])
     STAT_DECL(st_epi_full);
 #ifdef GMM_STATS
     const long long st_t0 = clock64();
 #endif
-    // wait for this tile's next accumulator, pull this warp's 32 lanes x 32 columns into registers, hand it back
-    auto fetch = [&](float (&v)[32]) {
+    // wait for this tile's next accumulator, pull its 64 columns of this warp's 32 lanes into registers, hand it back
+    auto fetch = [&](float (&va)[32], float (&vb)[32]) {
       const uint32_t abuf = job % kNumAcc;
       STAT_WAIT(st_epi_full, bar_acc_full + 8 * (2 * abuf + tile), (job / (2 * kNumAcc)) & 1);
       tc_fence_after();
+      const uint32_t taddr = taddr0 + abuf * FB_STAGE_N;
 #ifndef GMM_NO_LDTM
-      tc_ld32(taddr0 + abuf * FB_STAGE_N, v);
+      tc_ld32(taddr, va);
+      tc_ld32(taddr + 32, vb);
       tc_wait_ld();
 #else
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = (float)(i + job);
+      for (int i = 0; i < 32; ++i) { va[i] = (float)(i + job); vb[i] = (float)(i - job); }
 #endif
       tc_fence_before();
       __syncwarp();
@@ -456,15 +465,15 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       job += 2;
     };
     // The running (max, sum) of a row is kept over the whole run of consecutive stages this CTA computes for the same
-    // (rows[, model]) -- a "segment" -- so the cutoff is relative to the running maximum; one partial per segment and
-    // column half, stored at the index of the segment's first stage.
+    // (rows[, model]) -- a "segment" -- so the cutoff is relative to the running maximum; one partial per segment, stored
+    // at the index of the segment's first stage.
     const int n_run = kShared ? g.n_models : 1;
     int seg_start = 0, seg_row = 0, seg_model = 0;
     auto flush = [&]() {
       if constexpr (!kStore) {
         for (int r = 0; r < n_run; ++r) {
           const int mdl = kShared ? r : seg_model;
-          g.part[(((size_t)mdl * nst + seg_start) * 2 + half) * g.rows_cap + seg_row] = make_float2(mm[r], ss[r]);
+          g.part[((size_t)mdl * nst + seg_start) * g.rows_cap + seg_row] = make_float2(mm[r], ss[r]);
         }
       }
     };
@@ -480,50 +489,55 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         run_item = item;
         seg_start = stage; seg_row = row; seg_model = model;
       }
-      if constexpr (kShared) {
-        float q[32];                                    // the x^2 term Q of this (rows, 32 columns)
-        fetch(q);
+      {
+        if constexpr (kShared) {
+          float qa[32], qb[32];                         // the x^2 term Q of this (rows, 64-column stage)
+          fetch(qa, qb);
 #pragma unroll 1
-        for (int r = 0; r < g.n_models; ++r) {
-          float v[32];
-          fetch(v);
+          for (int r = 0; r < g.n_models; ++r) {
+            float va[32], vb[32];
+            fetch(va, vb);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 t = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(q[i], q[i + 1]));
-            v[i] = t.x; v[i + 1] = t.y;
+            for (int i = 0; i < 32; i += 2) {
+              const float2 t0 = __fadd2_rn(make_float2(va[i], va[i + 1]), make_float2(qa[i], qa[i + 1]));
+              const float2 t1 = __fadd2_rn(make_float2(vb[i], vb[i + 1]), make_float2(qb[i], qb[i + 1]));
+              va[i] = t0.x; va[i + 1] = t0.y; vb[i] = t1.x; vb[i + 1] = t1.y;
+            }
+            float m = mm[r], sacc = ss[r];
+#ifndef GMM_NO_LSE
+            lse_stage(va, vb, m, sacc);
+#else
+            m = fmaxf(m, va[0] + vb[31]);
+#endif
+            mm[r] = m;
+            ss[r] = sacc;
           }
-          float m = mm[r], sacc = ss[r];
-#ifndef GMM_NO_LSE
-          lse_stage(v, m, sacc);
-#else
-          m = fmaxf(m, v[0] + v[31]);
-#endif
-          mm[r] = m;
-          ss[r] = sacc;
-        }
-      } else {
-        float v[32];
-        fetch(v);
-        if constexpr (kStore) {
-          float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + stage * FB_STAGE_N + half * 32);
-          const float ln2 = 0.6931471805599453f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(v[i] * ln2, v[i + 1] * ln2, v[i + 2] * ln2, v[i + 3] * ln2);
         } else {
-          float m = mm[0], sacc = ss[0];
+          float va[32], vb[32];
+          fetch(va, vb);
+          if constexpr (kStore) {
+            float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + stage * FB_STAGE_N);
+            const float ln2 = 0.6931471805599453f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(va[i] * ln2, va[i + 1] * ln2, va[i + 2] * ln2, va[i + 3] * ln2);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) dst[8 + (i >> 2)] = make_float4(vb[i] * ln2, vb[i + 1] * ln2, vb[i + 2] * ln2, vb[i + 3] * ln2);
+          } else {
+            float m = mm[0], sacc = ss[0];
 #ifndef GMM_NO_LSE
-          lse_stage(v, m, sacc);
+            lse_stage(va, vb, m, sacc);
 #else
-          m = fmaxf(m, v[0] + v[31]);
+            m = fmaxf(m, va[0] + vb[31]);
 #endif
-          mm[0] = m;
-          ss[0] = sacc;
+            mm[0] = m;
+            ss[0] = sacc;
+          }
         }
       }
     }
     if (run_item >= 0) flush();
 #ifdef GMM_STATS
-    if (lane == 0 && (warp == 3 || warp == 7)) { g_gmm_stats[blockIdx.x * 16 + 10 + (warp == 7 ? 2 : 0)] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 11 + (warp == 7 ? 2 : 0)] = st_epi_full; }
+    if (lane == 0 && (warp == 2 || warp == 6)) { g_gmm_stats[blockIdx.x * 16 + 10 + (warp == 6 ? 2 : 0)] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 11 + (warp == 6 ? 2 : 0)] = st_epi_full; }
 #endif
   }
   tc_fence_before();
@@ -589,7 +603,7 @@ gmm_simt_kernel(const __half *__restrict__ a_img, const float *__restrict__ w_f3
       const float t = s_ll[r][k] - m;
       if (t >= -23.0f) s += exp2f(t);
     }
-    part[(((size_t)model * (2 * nch) + 2 * ch) * 2) * rows_cap + row0 + r] = make_float2(m, s);   // stage index of the chunk's first stage, half 0
+    part[((size_t)model * (2 * nch) + 2 * ch) * rows_cap + row0 + r] = make_float2(m, s);   // stage index of the chunk's first stage
   }
 }
 
@@ -609,7 +623,7 @@ gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, 
   // The partials of this row are the segments gmm_umma_kernel cut its stage sequence into: recompute the CTA boundaries
   // floor(total * b / grid) that fall inside this (super-tile[, model]) item.  umma_grid == 0: the fp32 cross-check kernel,
   // one partial per 128-column chunk.
-  float2 p[128];                                 // C <= 4096: at most 64 stages, hence at most 64 segments x 2 column halves
+  float2 p[64];                                  // C <= 4096: at most 64 stages, hence at most 64 segments
   int n = 0;
   if (umma_grid > 0) {
     const int n_super = (M + 2 * FB_TILE_M - 1) / (2 * FB_TILE_M);
@@ -621,12 +635,11 @@ gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, 
       const long long b = ((st + 1) * umma_grid - 1) / total;                 // the CTA whose range contains stage st
       long long end = total * (b + 1) / umma_grid;
       if (end > g0 + nst) end = g0 + nst;
-      p[n++] = part[(((size_t)model * nst + (int)(st - g0)) * 2) * rows_cap + row];
-      p[n++] = part[(((size_t)model * nst + (int)(st - g0)) * 2 + 1) * rows_cap + row];
+      p[n++] = part[((size_t)model * nst + (int)(st - g0)) * rows_cap + row];
       st = end;
     }
   } else {
-    for (int k = 0; k < nst; k += 2) p[n++] = part[(((size_t)model * nst + k) * 2) * rows_cap + row];
+    for (int k = 0; k < nst; k += 2) p[n++] = part[((size_t)model * nst + k) * rows_cap + row];
   }
   float mx = -INFINITY;
   for (int k = 0; k < n; ++k) mx = fmaxf(mx, p[k].x);

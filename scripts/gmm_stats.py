@@ -12,7 +12,7 @@ assert lib.fb_debug_gmm_stats(buf.ctypes.data) == 0
 t0 = buf[:, 0].min()
 print("kernel span (globaltimer, first entry -> last exit): %.1f us; entry skew max %.1f us" % (((buf[:, 0] + buf[:, 1]).max() - t0) / 1e3, (buf[:, 0].max() - t0) / 1e3))
 names = ["exit-entry ns", "setup clk", "total clk", "producer total", "producer wait", "issuer0 total", "issuer0 wait", "issuer1 total", "issuer1 wait",
-         "epi w2 total", "epi w2 wait", "epi w6 total", "epi w6 wait"]
+         "epi w3 total", "epi w3 wait", "epi w7 total", "epi w7 wait", "iss0 wait acc", "iss0 wait A"]
 for i, n in enumerate(names):
     c = buf[:, 1 + i]
     print("%-16s min %8d  median %8d  max %8d" % (n, c.min(), np.median(c), c.max()))
