@@ -48,6 +48,7 @@ _SIGS = {
     "fb_set_gmm_impl": (C.c_int, [_P, C.c_int]),
     "fb_score_gmm_host": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "fb_score_gmm_dev": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "fb_map_adapt_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, _P, _P, _P]),
     "fb_load_full_gmm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "fb_load_ivector_extractor": (C.c_int, [_P, _P, _P, C.c_double, C.c_int, C.c_int, C.c_int]),
     "fb_load_plda_backend": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfakebob_b200.so")
-SOURCES = ["fb_api.cu", "fb_frontend.cu", "fb_gmm.cu", "fb_nes.cu", "fb_comm.cu", "fb_ivector.cu"]
+SOURCES = ["fb_api.cu", "fb_frontend.cu", "fb_gmm.cu", "fb_nes.cu", "fb_comm.cu", "fb_ivector.cu", "fb_enroll.cu"]
 HEADERS = ["fb_common.cuh", "fb_nes.cuh", "fb_ivector.cuh", os.path.join("..", "..", "include", "fakebob_b200.h")]
 
 

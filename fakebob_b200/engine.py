@@ -63,6 +63,7 @@ class GmmEngine:
                              self.cfg.vad_proportion_threshold, self.cfg.vad_frames_context, self.cfg.cmn_window)
         _lib.check(self.lib.fb_set_feature_config(self.h, C.byref(fc)))
         self.n_models = len(gmm_params)
+        self._params = gmm_params
         for slot, g in enumerate(gmm_params):
             w = np.ascontiguousarray(g["weights"], dtype=np.float32)
             miv = np.ascontiguousarray(g["means_invvars"], dtype=np.float32)
@@ -105,6 +106,28 @@ class GmmEngine:
         self._last_B = B
         self._last_offsets = offsets
         return out
+
+    def map_adapt(self, audio_list, mean_tau=10.0):
+        """MAP mean-only adaptation of the (single) resident GMM -- the UBM -- to the pooled voiced frames of the
+        audios: gmm-global-acc-stats | gmm-global-est-map --update-flags=m (build_spk_models.py:202-219).
+        Returns dict(weights, means_invvars, inv_vars, gconsts, occupancy)."""
+        if self.n_models != 1:
+            raise ValueError("map_adapt needs an engine holding the UBM alone")
+        B = len(audio_list)
+        lens = np.array([a.shape[0] for a in audio_list], dtype=np.int64)
+        offsets = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        wave = np.ascontiguousarray(np.concatenate(audio_list) if B > 1 else audio_list[0], dtype=np.int16)
+        g = self._params[0]
+        Cn, D = g["means_invvars"].shape
+        miv = np.empty((Cn, D), dtype=np.float32)
+        gc = np.empty(Cn, dtype=np.float32)
+        occ = np.empty(Cn, dtype=np.float64)
+        _lib.check(self.lib.fb_map_adapt_host(self.h, _ptr(wave), _ptr(offsets), B, float(mean_tau), _ptr(miv), _ptr(gc), _ptr(occ)))
+        self._last_B = B
+        self._last_offsets = offsets
+        return {"weights": np.array(g["weights"], dtype=np.float32), "means_invvars": miv,
+                "inv_vars": np.array(g["inv_vars"], dtype=np.float32), "gconsts": gc, "occupancy": occ}
 
     def set_debug(self, on=True):
         _lib.check(self.lib.fb_set_debug(self.h, 1 if on else 0))

@@ -82,6 +82,16 @@ int fb_set_gmm_impl(fb_ctx *ctx, int impl);
 int fb_score_gmm_host(fb_ctx *ctx, const int16_t *wave, const int64_t *offsets, int B, double *out_avg_ll);
 int fb_score_gmm_dev(fb_ctx *ctx, const int16_t *wave_dev, const int64_t *offsets_host, int B, double *out_avg_ll_dev);
 
+/* ---- enrolment: serves build_spk_models.py step 2 ------------------------------------------------
+ * Replaces: `gmm-global-acc-stats --update-flags=m final.dubm <feats> acc` + `gmm-global-est-map --update-flags=m final.dubm
+ * acc <spk>-identity.gmm` (build_spk_models.py:202-219; gmm-global-est-map.cc is the reference's one native source file).
+ * MAP mean-only adaptation (MapDiagGmmUpdate, mean_tau = 10 by default in Kaldi) of slot 0 -- load the UBM alone,
+ * fb_finalize_gmms(ctx, 1) -- to the voiced frames of the batch, all utterances pooled like one feature archive.
+ * Weights and variances are kept.  out_means_invvars: C x 72 float32, out_gconsts: C float32 (DiagGmm members, ready for
+ * fb_load_diag_gmm or a Kaldi model file), out_occupancy: C float64 or NULL. */
+int fb_map_adapt_host(fb_ctx *ctx, const int16_t *wave, const int64_t *offsets, int B, double mean_tau,
+                      float *out_means_invvars, float *out_gconsts, double *out_occupancy);
+
 /* ---- i-vector / PLDA scoring: serves iv_{CSI,OSI,SV}.score() ---------------------------------
  * Replaces: ivector_PLDA_kaldiHelper.score() (ivector_PLDA_kaldiHelper.py:340-363): write_audio, data_prepare, make_mfcc,
  * compute_vad, extract_ivector (sid/extract_ivectors.sh, :202-211), write_trials, plda_scoring (:251-280), resolve_score.

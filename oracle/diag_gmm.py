@@ -77,15 +77,34 @@ class DiagGmm:
         p = np.exp(ll)
         return p / p.sum(axis=1, keepdims=True)
 
+    def component_posteriors(self, X):
+        """DiagGmm::ComponentPosteriors (gmm/diag-gmm.cc): float log-likelihoods, then VectorBase<float>::ApplySoftMax
+        (float max, float exp, float running sum in index order, one float scale)."""
+        ll = self.loglikes(X)
+        mx = ll.max(axis=1, keepdims=True)
+        e = np.exp((ll - mx).astype(F32)).astype(F32)
+        s = np.cumsum(e, axis=1, dtype=F32)[:, -1:]
+        return (e * (F32(1.0) / s).astype(F32)).astype(F32)
+
     def map_adapt_means(self, X, tau=10.0):
-        """gmm-global-acc-stats + gmm-global-est-map --update-flags=m (mean_tau=10)."""
-        post = self.posteriors(X)                         # (T, C) double
-        occ = post.sum(axis=0)                            # (C,)
-        mean_acc = post.T @ np.asarray(X, dtype=np.float64)
+        """gmm-global-acc-stats --update-flags=m + gmm-global-est-map --update-flags=m (build_spk_models.py:202-219; the
+        reference's gmm-global-est-map.cc calls MapDiagGmmUpdate, mean_tau = 10): AccumDiagGmm::AccumulateFromPosteriors
+        adds post_d[c] and post_d[c] * x_d per frame in double, frame order; MapDiagGmmUpdate sets
+        mean = (mean_acc + tau * old_mean) / (occ + tau); weights and variances stay; ComputeGconsts."""
+        post = self.component_posteriors(X).astype(np.float64)            # (T, C)
+        X64 = np.asarray(np.asarray(X, dtype=F32), dtype=np.float64)
+        C, D = self.means_invvars.shape
+        occ = np.zeros(C)
+        mean_acc = np.zeros((C, D))
+        for t in range(post.shape[0]):
+            occ += post[t]
+            mean_acc += post[t][:, None] * X64[t][None, :]
         old = self.means()
-        new = (mean_acc + tau * old) / (occ + tau)[:, None]
+        new = (mean_acc + tau * old) * (1.0 / (occ + tau))[:, None]
         iv = self.inv_vars.astype(np.float64)
-        return DiagGmm(self.weights, (new * iv).astype(F32), self.inv_vars)
+        out = DiagGmm(self.weights, (new * iv).astype(F32), self.inv_vars)
+        out.occupancy = occ
+        return out
 
 
 def log_sum_exp_rows(ll):
