@@ -378,147 +378,208 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per utterance: A = unpack(quad) + I, rhs = sum of lin partials (+ prior offset on element 0), blocked Cholesky
-// (panel width 32 in shared memory, rank-32 trailing updates), blocked forward / backward substitution.
-// One CTA (512 threads) per utterance; A lives in global scratch [b][R][R] (L2 resident), lower triangle only.
+// Per utterance: A = unpack(quad) + I, rhs = sum of lin partials (+ prior offset on element 0), right-looking blocked
+// Cholesky (block 32) with the right-hand side carried as an extra matrix row, so the forward substitution falls out of the
+// factorisation; blocked backward substitution.  One CTA (512 threads) per utterance; A lives in global scratch
+// [b][R][R] (L2 resident), lower triangle only.  Per block column (all float64, reciprocal diagonal like LAPACK dpotf2):
+//   diagonal block   warp 0, one row per lane in registers, shuffles (no shared-memory round trips)
+//   L21 = A21 L11^-T one thread per row, the row in registers, L11 broadcast from shared memory
+//   trailing update  warp tiles of 8 rows x 128 columns (lane owns columns l, l+32, l+64, l+96: conflict-free panel reads,
+//                    coalesced global read-modify-write), 32 accumulators per lane
 // ------------------------------------------------------------------------------------------------
 #define IV_NB 32
-#define IV_PSTRIDE 33      // padded panel row stride (doubles): rows map to different banks
+#define IV_PSTRIDE 33      // padded panel row stride (doubles): consecutive rows map to different banks
 
 __global__ void __launch_bounds__(512)
 ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ lin_part, int n_splits, int B, int R, int n_packed,
                   double prior_offset, double *__restrict__ Awork, float *__restrict__ ivec, int *__restrict__ err,
                   const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
+#ifdef IV_SOLVE_STATS
+  long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long st_t = clock64();
+#define IV_LAP(i) do { const long long n_ = clock64(); st[i] += n_ - st_t; st_t = n_; } while (0)
+#else
+#define IV_LAP(i)
+#endif
   extern __shared__ double s_dyn[];
-  double *rhs = s_dyn;                               // [R]
-  double *panel = s_dyn + R;                         // [R][IV_PSTRIDE]  rows k0..R-1 of the current block column
+  double *rhs = s_dyn;                               // [R]   right-hand side -> y -> w
+  double *invd = s_dyn + R;                          // [R]   1 / L[k][k]
+  double *panel = s_dyn + 2 * R;                     // [R + 2][IV_PSTRIDE]: rows k0..R-1 of the block column, the rhs row, a zero row
+  __shared__ double s_l11[IV_NB][IV_PSTRIDE];        // factored diagonal block, identity-padded to 32 x 32
+  __shared__ double s_invd[IV_NB];
   __shared__ double s_blk[IV_NB];
   __shared__ int s_fail;
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   double *A = Awork + (size_t)b * R * R;
   if (tid == 0) s_fail = 0;
-  for (int idx = tid; idx < R * R; idx += nt) {
-    const int i = idx / R, j = idx - i * R;
-    if (j <= i) A[idx] = quad[(size_t)b * n_packed + (size_t)i * (i + 1) / 2 + j] + ((i == j) ? 1.0 : 0.0);
-  }
+  // A = unpack(quad) + I is never materialised: block column 0 is loaded straight from the packed triangle and the first
+  // trailing update writes quad + I - L21 L21^T instead of updating in place.
+  const double *qb = quad + (size_t)b * n_packed;
   for (int r = tid; r < R; r += nt) {
     double acc = 0.0;
+#pragma unroll 8
     for (int s = 0; s < n_splits; ++s) acc += lin_part[((size_t)s * B + b) * R + r];
     rhs[r] = acc + ((r == 0) ? prior_offset : 0.0);
   }
   __syncthreads();
+  IV_LAP(0);
   for (int k0 = 0; k0 < R; k0 += IV_NB) {
     const int nbk = min(IV_NB, R - k0);
-    const int rows = R - k0;                         // panel rows (global rows k0..R-1)
-    // load block column
-    for (int idx = tid; idx < rows * nbk; idx += nt) {
-      const int i = idx / nbk, j = idx - i * nbk;
-      panel[i * IV_PSTRIDE + j] = (k0 + j <= k0 + i) ? A[(size_t)(k0 + i) * R + k0 + j] : 0.0;
+    const int rows = R - k0;                         // matrix rows in the panel (global rows k0..R-1); local row `rows` = rhs
+    const int zrow = rows + 1;                       // all-zero row: target of out-of-range tile rows
+    // ---- load the block column (columns beyond nbk are zero), the rhs block and the zero row.  Branch-free body so that
+    // the unrolled loads are in flight together (the loop is L2-latency bound); entries above the diagonal are read
+    // (never-written scratch) and discarded.
+    if (k0 == 0) {
+#pragma unroll 4
+      for (int idx = tid; idx < rows * IV_NB; idx += nt) {
+        const int i = idx >> 5, j = idx & 31;
+        const bool use = j < nbk && j <= i;
+        const double v = qb[use ? (size_t)i * (i + 1) / 2 + j : 0];
+        panel[i * IV_PSTRIDE + j] = use ? v + ((i == j) ? 1.0 : 0.0) : 0.0;
+      }
+    } else {
+#pragma unroll 8
+      for (int idx = tid; idx < rows * IV_NB; idx += nt) {
+        const int i = idx >> 5, j = idx & 31;
+        const bool use = j < nbk && j <= i;
+        const double v = A[(size_t)(k0 + i) * R + k0 + (j < nbk ? j : 0)];
+        panel[i * IV_PSTRIDE + j] = use ? v : 0.0;
+      }
+    }
+    if (tid < 2 * IV_NB) {
+      const int i = rows + (tid >> 5), j = tid & 31;
+      panel[i * IV_PSTRIDE + j] = (i == rows && j < nbk) ? rhs[k0 + j] : 0.0;
     }
     __syncthreads();
-    // factor the diagonal block (warp 0), unblocked
+    IV_LAP(1);
+    // ---- diagonal block: warp 0, row `lane` in registers (identity padding for nbk < 32)
     if (warp == 0) {
-      for (int k = 0; k < nbk; ++k) {
-        const double akk = panel[k * IV_PSTRIDE + k];
-        if (!(akk > 0.0)) { if (lane == 0) s_fail = 1; break; }
-        const double d = sqrt(akk);
-        __syncwarp();
-        if (lane == k) panel[k * IV_PSTRIDE + k] = d;
-        if (lane > k && lane < nbk) panel[lane * IV_PSTRIDE + k] /= d;
-        __syncwarp();
-        // trailing update inside the block: element (i = lane, j) for k < j <= i
-        if (lane > k && lane < nbk) {
-          const double lik = panel[lane * IV_PSTRIDE + k];
-          for (int j = k + 1; j <= lane; ++j) panel[lane * IV_PSTRIDE + j] -= lik * panel[j * IV_PSTRIDE + k];
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    if (s_fail) { if (tid == 0) atomicExch(err, 3); return; }
-    // rows below the diagonal block: L21 = A21 * L11^-T (one thread per row, forward substitution over the block)
-    for (int i = nbk + tid; i < rows; i += nt) {
-      double *row = panel + i * IV_PSTRIDE;
-      for (int j = 0; j < nbk; ++j) {
-        double v = row[j];
-        for (int q = 0; q < j; ++q) v -= row[q] * panel[j * IV_PSTRIDE + q];
-        row[j] = v / panel[j * IV_PSTRIDE + j];
-      }
-    }
-    __syncthreads();
-    // write the factored block column back
-    for (int idx = tid; idx < rows * nbk; idx += nt) {
-      const int i = idx / nbk, j = idx - i * nbk;
-      if (j <= i) A[(size_t)(k0 + i) * R + k0 + j] = panel[i * IV_PSTRIDE + j];
-    }
-    // trailing update A22 -= L21 L21^T on the lower triangle: 4x4 register tiles
-    const int rem = rows - nbk;                      // trailing dimension
-    const int nt4 = (rem + 3) / 4;
-    const int n_tiles = nt4 * (nt4 + 1) / 2;
-    for (int t = tid; t < n_tiles; t += nt) {
-      int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-      while (ti * (ti + 1) / 2 > t) --ti;
-      const int tj = t - ti * (ti + 1) / 2;
-      const int i0 = nbk + ti * 4, j0 = nbk + tj * 4;       // panel-local row indices
-      double c[4][4];
+      double l[IV_NB];
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) c[x][y] = 0.0;
-      for (int q = 0; q < nbk; ++q) {
-        double av[4], bv[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          av[x] = (i0 + x < rows) ? panel[(i0 + x) * IV_PSTRIDE + q] : 0.0;
-          bv[x] = (j0 + x < rows) ? panel[(j0 + x) * IV_PSTRIDE + q] : 0.0;
-        }
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) c[x][y] += av[x] * bv[y];
-      }
-#pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-          const int gi = k0 + i0 + x, gj = k0 + j0 + y;
-          if (gi < R && gj <= gi && gj < R) A[(size_t)gi * R + gj] -= c[x][y];
-        }
-    }
-    __syncthreads();
-  }
-  // forward substitution L y = rhs, blocked
-  for (int k0 = 0; k0 < R; k0 += IV_NB) {
-    const int nbk = min(IV_NB, R - k0);
-    if (warp == 0) {
-      double yv = (lane < nbk) ? rhs[k0 + lane] : 0.0;
-      double lrow[IV_NB];                              // row `lane` of the diagonal block
-#pragma unroll
-      for (int k = 0; k < IV_NB; ++k) lrow[k] = (lane < nbk && k <= lane) ? A[(size_t)(k0 + lane) * R + k0 + k] : 1.0;
+      for (int k = 0; k < IV_NB; ++k)
+        l[k] = (lane < nbk && k < nbk) ? ((k <= lane) ? panel[lane * IV_PSTRIDE + k] : 0.0) : ((k == lane) ? 1.0 : 0.0);
+      bool ok = true;
+      double my_inv = 1.0;
 #pragma unroll
       for (int k = 0; k < IV_NB; ++k) {
-        if (k < nbk) {
-          const double lkk = __shfl_sync(0xffffffffu, lrow[k], k);
-          const double yk = __shfl_sync(0xffffffffu, yv, k) / lkk;
-          if (lane == k) yv = yk;
-          if (lane > k && lane < nbk) yv -= lrow[k] * yk;
+        const double akk = __shfl_sync(0xffffffffu, l[k], k);
+        if (!(akk > 0.0)) ok = false;
+        const double inv = rsqrt(akk);
+        if (lane == k) { l[k] = akk * inv; my_inv = inv; }
+        else if (lane > k) l[k] *= inv;
+#pragma unroll
+        for (int j = 0; j < IV_NB; ++j) {             // constant trip count so that the nest unrolls fully (l[] stays in registers)
+          if (j > k) {
+            const double ljk = __shfl_sync(0xffffffffu, l[k], j);
+            if (lane >= j) l[j] -= l[k] * ljk;
+          }
         }
       }
-      if (lane < nbk) { rhs[k0 + lane] = yv; s_blk[lane] = yv; }
+      if (!ok && lane == 0) s_fail = 1;
+#pragma unroll
+      for (int k = 0; k < IV_NB; ++k) {
+        s_l11[lane][k] = (k <= lane) ? l[k] : 0.0;
+        if (lane < nbk && k <= lane && k < nbk) panel[lane * IV_PSTRIDE + k] = l[k];
+      }
+      s_invd[lane] = my_inv;
+      if (lane < nbk) invd[k0 + lane] = my_inv;
     }
     __syncthreads();
-    for (int i = k0 + nbk + tid; i < R; i += nt) {
-      double v = rhs[i];
-      const double *row = A + (size_t)i * R + k0;
-      for (int j = 0; j < nbk; ++j) v -= row[j] * s_blk[j];
-      rhs[i] = v;
+    IV_LAP(2);
+    if (s_fail) { if (tid == 0) atomicExch(err, 3); return; }
+    // ---- rows below the diagonal block and the rhs row: x = a L11^-T, the row in registers
+    for (int i = nbk + tid; i <= rows; i += nt) {
+      double *row = panel + i * IV_PSTRIDE;
+      double x[IV_NB];
+#pragma unroll
+      for (int j = 0; j < IV_NB; ++j) x[j] = row[j];
+      // column-oriented: once x[q] is final, every later entry takes its update (31 - q independent FMAs); the empty asm
+      // keeps the compiler from hoisting all 496 broadcast loads of L11 to the top (it spilled 4 KB per thread)
+#pragma unroll
+      for (int q = 0; q < IV_NB; ++q) {
+        x[q] *= s_invd[q];
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < IV_NB; ++j)
+          if (j > q) x[j] -= x[q] * s_l11[j][q];
+      }
+#pragma unroll
+      for (int j = 0; j < IV_NB; ++j) row[j] = x[j];
     }
     __syncthreads();
+    IV_LAP(3);
+    // ---- rhs: y block out, trailing part updated (the extra row of the trailing update)
+    const double *yrow = panel + rows * IV_PSTRIDE;
+    for (int j = tid; j < rows; j += nt) {
+      if (j < nbk) {
+        rhs[k0 + j] = yrow[j];
+      } else {
+        double v = rhs[k0 + j];
+        const double *lr = panel + j * IV_PSTRIDE;
+#pragma unroll 8
+        for (int q = 0; q < IV_NB; ++q) v -= yrow[q] * lr[q];
+        rhs[k0 + j] = v;
+      }
+    }
+    // ---- write the factored block column back
+    for (int idx = tid; idx < rows * IV_NB; idx += nt) {
+      const int i = idx >> 5, j = idx & 31;
+      if (j < nbk && j <= i) A[(size_t)(k0 + i) * R + k0 + j] = panel[i * IV_PSTRIDE + j];
+    }
+    IV_LAP(4);
+    // ---- trailing update A22 -= L21 L21^T on the lower triangle: warp tiles of 8 rows x 128 columns
+    const int rem = rows - nbk;
+    if (rem > 0) {
+      const int nrb = (rem + 7) >> 3, ncb = (rem + 127) >> 7;
+      int n_items = 0;
+      for (int cb = 0; cb < ncb; ++cb) n_items += nrb - 16 * cb;
+      for (int it = warp; it < n_items; it += nw) {
+        int cb = 0, rb = it;
+        while (rb >= nrb - 16 * cb) { rb -= nrb - 16 * cb; ++cb; }
+        rb += 16 * cb;
+        const int i0 = nbk + 8 * rb, j0 = nbk + 128 * cb;          // panel-local rows
+        int ri[8], rj[4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) ri[x] = ((i0 + x < rows) ? i0 + x : zrow) * IV_PSTRIDE;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) rj[y] = ((j0 + lane + 32 * y < rows) ? j0 + lane + 32 * y : zrow) * IV_PSTRIDE;
+        double c[8][4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) c[x][y] = 0.0;
+#pragma unroll 8
+        for (int q = 0; q < IV_NB; ++q) {
+          double av[8], bv[4];
+#pragma unroll
+          for (int x = 0; x < 8; ++x) av[x] = panel[ri[x] + q];
+#pragma unroll
+          for (int y = 0; y < 4; ++y) bv[y] = panel[rj[y] + q];
+#pragma unroll
+          for (int x = 0; x < 8; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) c[x][y] += av[x] * bv[y];
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) {
+            const int li = i0 + x, lj = j0 + lane + 32 * y;
+            if (li < rows && lj <= li) {
+              double *dst = A + (size_t)(k0 + li) * R + k0 + lj;
+              const double old = (k0 == 0) ? qb[(size_t)li * (li + 1) / 2 + lj] + ((li == lj) ? 1.0 : 0.0) : *dst;
+              *dst = old - c[x][y];
+            }
+          }
+      }
+    }
+    __syncthreads();
+    IV_LAP(5);
   }
-  // backward substitution L^T w = y, blocked from the last block
+  // rhs now holds y = L^-1 b.  Backward substitution L^T w = y, blocked from the last block.
   const int n_blocks = (R + IV_NB - 1) / IV_NB;
   for (int bi = n_blocks - 1; bi >= 0; --bi) {
     const int k0 = bi * IV_NB;
@@ -527,12 +588,12 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
       double wv = (lane < nbk) ? rhs[k0 + lane] : 0.0;
       double lcol[IV_NB];                              // column `lane` of the diagonal block
 #pragma unroll
-      for (int k = 0; k < IV_NB; ++k) lcol[k] = (k < nbk && lane <= k) ? A[(size_t)(k0 + k) * R + k0 + lane] : 1.0;
+      for (int k = 0; k < IV_NB; ++k) lcol[k] = (k < nbk && lane < k) ? A[(size_t)(k0 + k) * R + k0 + lane] : 0.0;
+      const double my_inv = (lane < nbk) ? invd[k0 + lane] : 1.0;
 #pragma unroll
       for (int k = IV_NB - 1; k >= 0; --k) {
         if (k < nbk) {
-          const double lkk = __shfl_sync(0xffffffffu, lcol[k], k);
-          const double wk = __shfl_sync(0xffffffffu, wv, k) / lkk;
+          const double wk = __shfl_sync(0xffffffffu, wv * my_inv, k);
           if (lane == k) wv = wk;
           if (lane < k) wv -= lcol[k] * wk;
         }
@@ -547,8 +608,13 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
     }
     __syncthreads();
   }
+  IV_LAP(6);
+#ifdef IV_SOLVE_STATS
+  if (b == 0 && (tid == 0 || tid == 511))
+    printf("solve tid %d clk: init %lld load %lld diag %lld l21 %lld rhs+wb %lld trailing %lld backsub %lld\n", tid, st[0], st[1], st[2], st[3],
+           st[4], st[5], st[6]);
+#endif
   for (int r = tid; r < R; r += nt) ivec[(size_t)b * R + r] = (float)(rhs[r] - ((r == 0) ? prior_offset : 0.0));
-  (void)nw;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -900,7 +966,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, B, v->C, v->n_packed,
                                                                                    v->quad.p, done_flag);
   fb_prof_mark(ctx, 12);
-  const size_t smem_solve = ((size_t)v->R + (size_t)v->R * IV_PSTRIDE) * sizeof(double);
+  const size_t smem_solve = (2 * (size_t)v->R + ((size_t)v->R + 2) * IV_PSTRIDE) * sizeof(double);
   static bool attr_solve = false;
   if (!attr_solve) {
     FB_CUDA(cudaFuncSetAttribute(ivec_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
