@@ -320,12 +320,17 @@ ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, 
 }
 
 // quad: grid (ceil(n_packed / 256), ceil(B/32)); block 256 = 4 utterance-groups x 64 column-groups of 4 packed entries.
-__global__ void __launch_bounds__(256)
+// The kernel streams U (C x n_packed fp32, 657 MB at C = 2048, R = 400) from HBM with one 16-byte load per thread and
+// component, so it is latency bound unless several loads are in flight: the active components of a 64-component chunk are
+// compacted into a list and processed four at a time with their loads issued up front.
+__global__ void __launch_bounds__(256, 2)
 ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, int B, int C, int n_packed,
                  double *__restrict__ quad, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
   __shared__ __align__(16) double s_g[64][IV_BCHUNK];
   __shared__ int s_any[64];
+  __shared__ int s_list[64 + 4];
+  __shared__ int s_n;
   const int b0 = blockIdx.y * IV_BCHUNK;
   const int nb = min(IV_BCHUNK, B - b0);
   const int ug = threadIdx.x >> 6, cg = threadIdx.x & 63;
@@ -336,6 +341,25 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  auto load_row = [&](int c, float (&p)[4]) {
+    const float *row = U + (size_t)c * n_packed + e0;
+    if (vec_ok) {
+      const float4 q = __ldcs(reinterpret_cast<const float4 *>(row));      // streamed once: do not keep in L2
+      p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = (e0 + i < n_packed) ? row[i] : 0.f;
+    }
+  };
+  auto fma_row = [&](int k, const float (&p)[4]) {
+    const double2 *gr = reinterpret_cast<const double2 *>(&s_g[k][ug * 8]);
+    const double2 g01 = gr[0], g23 = gr[1], g45 = gr[2], g67 = gr[3];
+    const double gv[8] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y, g67.x, g67.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] += (double)p[i] * gv[j];
+  };
   for (int cb = 0; cb < C; cb += 64) {
     __syncthreads();
     if (threadIdx.x < 64) s_any[threadIdx.x] = 0;
@@ -347,25 +371,29 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
       if (g != 0.0) s_any[k] = 1;
     }
     __syncthreads();
-    const int kmax = min(64, C - cb);
-    for (int k = 0; k < kmax; ++k) {
-      if (!s_any[k]) continue;
-      const float *row = U + (size_t)(cb + k) * n_packed + e0;
+    if (threadIdx.x < 32) {                       // ordered compaction of the active components (ascending k, like the plain loop)
+      const int lane = threadIdx.x;
+      const unsigned m0 = __ballot_sync(0xffffffffu, s_any[lane] != 0);
+      const unsigned m1 = __ballot_sync(0xffffffffu, s_any[32 + lane] != 0);
+      const unsigned below = (1u << lane) - 1u;
+      if (m0 & (1u << lane)) s_list[__popc(m0 & below)] = lane;
+      if (m1 & (1u << lane)) s_list[__popc(m0) + __popc(m1 & below)] = 32 + lane;
+      if (lane == 0) s_n = __popc(m0) + __popc(m1);
+    }
+    __syncthreads();
+    const int n = s_n;
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+      const int k0 = s_list[i], k1 = s_list[i + 1], k2 = s_list[i + 2], k3 = s_list[i + 3];
+      float p0[4], p1[4], p2[4], p3[4];
+      load_row(cb + k0, p0); load_row(cb + k1, p1); load_row(cb + k2, p2); load_row(cb + k3, p3);
+      fma_row(k0, p0); fma_row(k1, p1); fma_row(k2, p2); fma_row(k3, p3);
+    }
+    for (; i < n; ++i) {
+      const int k = s_list[i];
       float p[4];
-      if (vec_ok) {
-        const float4 q = *reinterpret_cast<const float4 *>(row);
-        p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = (e0 + i < n_packed) ? row[i] : 0.f;
-      }
-      const double2 *gr = reinterpret_cast<const double2 *>(&s_g[k][ug * 8]);
-      const double2 g01 = gr[0], g23 = gr[1], g45 = gr[2], g67 = gr[3];
-      const double gv[8] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y, g67.x, g67.y};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] += (double)p[i] * gv[j];
+      load_row(cb + k, p);
+      fma_row(k, p);
     }
   }
 #pragma unroll
