@@ -136,6 +136,165 @@ fgmm_post_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Same arithmetic, rows grouped: one CTA handles the rows of EIGHT audios at the same frame index t, one warp per row.
+// The plain kernel above executes ~9 instructions per (row, component, packed entry) -- table lookup, two feature loads,
+// products, select -- and gathers 20 x 10.5 KB of packed inverse covariances per row from L2 (4.8 GB per NES iteration at
+// C3).  Here every lane keeps its 83 products x_r x_c (halved on the diagonal) of the row in REGISTERS, so a component costs
+// one shared-memory load and one FMA per entry, and each covariance is staged in shared memory once (cp.async, double
+// buffered) for all rows of the CTA that selected it: the audios of an NES batch are perturbations of one utterance, so
+// rows with the same frame index select (almost) the same components.  Any batch is handled correctly: rows that share no
+// component simply do not share loads.  Per row the operations and their order are those of fgmm_post_kernel.
+// ------------------------------------------------------------------------------------------------
+#define IV_GROUP 8
+#define IV_PACKED_PAD ((IV_PACKED + 3) & ~3)
+#define IV_XX_REGS ((IV_PACKED + 31) / 32)          // 83
+#define IV_POST_STAGES 4                            // covariance blocks in flight: an L2 round trip (~1 us) per 0.3 us of compute
+static_assert(IV_PACKED % 4 == 0 && FB_DIM % 4 == 0, "16-byte cp.async needs 16-byte aligned component blocks");
+
+__global__ void __launch_bounds__(256)
+fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, const float *__restrict__ gconsts,
+                       const float *__restrict__ means_invcovars, const float *__restrict__ inv_covars_packed,
+                       const unsigned short *__restrict__ rc_table, const int *__restrict__ frame_off,
+                       const int *__restrict__ vrank, const int *__restrict__ row_off, int B, int C, int n_chunks,
+                       float min_post, float *__restrict__ post, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  __shared__ __align__(16) float s_S[IV_POST_STAGES][IV_PACKED_PAD];
+  __shared__ __align__(16) float s_mic[IV_POST_STAGES][FB_DIM];
+  __shared__ float s_x[IV_GROUP][FB_DIM];
+  __shared__ unsigned s_bitmap[128];                  // C <= 4096
+  __shared__ int s_list[IV_GROUP * IV_NSEL];
+  __shared__ int s_n;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x / n_chunks, chunk = blockIdx.x - t * n_chunks;
+  // row of this warp: audio chunk * 8 + w at frame index t, -1 = not voiced / beyond the utterance
+  int row = -1;
+  {
+    const int b = chunk * IV_GROUP + w;
+    if (b < B) {
+      const int f0 = frame_off[b];
+      if (t < frame_off[b + 1] - f0) {
+        const int r = vrank[f0 + t];
+        if (r >= 0) row = row_off[b] + r;
+      }
+    }
+  }
+  if (threadIdx.x < 128) s_bitmap[threadIdx.x] = 0u;
+  const int sel = (row >= 0 && lane < IV_NSEL) ? gsel[(size_t)row * IV_NSEL + lane] : -1;
+  for (int d = lane; d < FB_DIM; d += 32) s_x[w][d] = (row >= 0) ? feats[(size_t)row * FB_DIM + d] : 0.f;
+  __syncthreads();
+  if (sel >= 0) atomicOr(&s_bitmap[sel >> 5], 1u << (sel & 31));
+  // this row's products, in the lane's registers: entry e = lane + 32 m
+  float xx[IV_XX_REGS];
+#pragma unroll
+  for (int m = 0; m < IV_XX_REGS; ++m) {
+    const int e = lane + 32 * m;
+    float v = 0.f;
+    if (e < IV_PACKED) {
+      const unsigned short rc = rc_table[e];
+      const int rr = rc >> 8, cc = rc & 255;
+      const float p = s_x[w][rr] * s_x[w][cc];
+      v = (rr == cc) ? 0.5f * p : p;
+    }
+    xx[m] = v;
+  }
+  __syncthreads();
+  if (w == 0) {                                       // ordered list of the components any row of the CTA selected
+    const int nw = (C + 31) >> 5;                     // bitmap words, 4 per lane
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt += (lane * 4 + k < nw) ? __popc(s_bitmap[lane * 4 + k]) : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    int pos = incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (lane * 4 + k < nw) {
+        unsigned bits = s_bitmap[lane * 4 + k];
+        while (bits) {
+          const int bpos = __ffs(bits) - 1;
+          bits &= bits - 1;
+          s_list[pos++] = (lane * 4 + k) * 32 + bpos;
+        }
+      }
+    }
+    if (lane == 31) s_n = incl;
+  }
+  __syncthreads();
+  const int n_union = s_n;
+  if (n_union == 0) return;
+  auto stage = [&](int ui) {                          // cp.async of component s_list[ui] into buffer ui % IV_POST_STAGES
+    if (ui < n_union) {
+      const int c = s_list[ui];
+      const float4 *S = reinterpret_cast<const float4 *>(inv_covars_packed + (size_t)c * IV_PACKED);
+      float4 *dst = reinterpret_cast<float4 *>(s_S[ui % IV_POST_STAGES]);
+      for (int e = threadIdx.x; e < IV_PACKED / 4; e += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + e)), "l"(S + e) : "memory");
+      if (threadIdx.x < FB_DIM / 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                     ::"r"((unsigned)__cvta_generic_to_shared(reinterpret_cast<float4 *>(s_mic[ui % IV_POST_STAGES]) + threadIdx.x)),
+                       "l"(reinterpret_cast<const float4 *>(means_invcovars + (size_t)c * FB_DIM) + threadIdx.x) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");      // (possibly empty) group: keeps the group count uniform
+  };
+  float my_ll = -INFINITY;
+#pragma unroll
+  for (int s0 = 0; s0 < IV_POST_STAGES - 1; ++s0) stage(s0);
+  for (int ui = 0; ui < n_union; ++ui) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(IV_POST_STAGES - 2) : "memory");   // this thread's part of component ui landed
+    __syncthreads();                                  // ... everybody's did, and everybody finished component ui - 1
+    stage(ui + IV_POST_STAGES - 1);                   // into the buffer component ui - 1 used
+    const int c = s_list[ui];
+    const int pos = __ffs(__ballot_sync(0xffffffffu, sel == c)) - 1;
+    if (pos >= 0) {
+      const float *S = s_S[ui % IV_POST_STAGES];
+      float q = 0.f;
+#pragma unroll
+      for (int m = 0; m < IV_XX_REGS; ++m) {
+        const int e = lane + 32 * m;
+        if (e < IV_PACKED) q += S[e] * xx[m];
+      }
+      float lin = 0.f;
+      for (int d = lane; d < FB_DIM; d += 32) lin += s_mic[ui % IV_POST_STAGES][d] * s_x[w][d];
+      float tot = lin - q;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane == pos) my_ll = gconsts[c] + tot;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (row < 0) return;
+  // softmax / pruning, exactly as in fgmm_post_kernel
+  float m = my_ll;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float e = (lane < IV_NSEL) ? expf(my_ll - m) : 0.f;
+  float sum = 0.f;
+  for (int j = 0; j < IV_NSEL; ++j) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, e, j));
+  float p = e * (float)(1.0 / (double)sum);
+  if (min_post != 0.f) {
+    float bv = (lane < IV_NSEL) ? p : -1.f;
+    int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+    }
+    if (p < min_post) p = 0.f;
+    double s2 = 0.0;
+    for (int j = 0; j < IV_NSEL; ++j) s2 += (double)__shfl_sync(0xffffffffu, p, j);
+    const float s2f = (float)s2;
+    if (s2f == 0.f) p = (lane == bl) ? 1.f : 0.f;
+    else p = p * (float)(1.0 / (double)s2f);
+  }
+  if (lane < IV_NSEL) post[(size_t)row * IV_NSEL + lane] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Baum-Welch statistics per utterance: gamma[b][c], X[b][c][72] (float64, dense).  One CTA per utterance.
 // Pairs are bucketed by component in shared memory, each bucket is put in frame order (rank sort), then one warp
 // per component accumulates sequentially -- the same order as Kaldi's per-frame AccStats, deterministic.
@@ -966,9 +1125,17 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   if ((rc = fb_run_gmm_store(ctx, v->ll.p, done_flag))) return rc;
   gselect_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(v->ll.p, ctx->misc.p, v->C, v->gsel.p, done_flag);
   fb_prof_mark(ctx, 8);
-  fgmm_post_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->gconsts.p, v->means_invcovars.p,
-                                                                  v->inv_covars.p, v->rc_table.p, ctx->misc.p, v->min_post, v->post.p,
-                                                                  done_flag);
+  static const bool plain_post = getenv("FB_IV_PLAIN_POST") != nullptr;       // diagnostic: the one-row-per-warp kernel
+  if (plain_post) {
+    fgmm_post_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->gconsts.p, v->means_invcovars.p,
+                                                                    v->inv_covars.p, v->rc_table.p, ctx->misc.p, v->min_post, v->post.p,
+                                                                    done_flag);
+  } else {
+    const int n_chunks = fb_div_up(B, IV_GROUP);
+    fgmm_post_group_kernel<<<ctx->max_frames * n_chunks, 256, 0, ctx->stream>>>(
+        ctx->feats_f32.p, v->gsel.p, v->gconsts.p, v->means_invcovars.p, v->inv_covars.p, v->rc_table.p, ctx->frame_off.p,
+        ctx->vrank.p, ctx->row_off.p, B, v->C, n_chunks, v->min_post, v->post.p, done_flag);
+  }
   fb_prof_mark(ctx, 9);
   const int max_pairs = ctx->max_frames * IV_NSEL;
   const size_t smem_stats = (size_t)(3 * v->C + 1) * sizeof(int) + (size_t)(2 * max_pairs + 2) * sizeof(unsigned short) +
