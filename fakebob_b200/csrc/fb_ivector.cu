@@ -27,12 +27,20 @@ int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag);
 // ------------------------------------------------------------------------------------------------
 // Top-20 Gaussian selection: one warp per frame; lanes hold C/32 values each (C <= 2048).
 // Ties resolve to the lower component index (stable descending sort).
+// Fast path: bisect a threshold below the row maximum until between 20 and 64 values pass it (a few counting passes),
+// compact those candidates into shared memory and rank them exactly (value descending, index ascending).  Rows where the
+// bisection does not settle (massive ties) take the plain 20-round arg-max selection.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+#define IV_CAND 64
+
+__global__ void __launch_bounds__(256, 2)
 gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C, int *__restrict__ gsel,
                const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  __shared__ float s_val[8][IV_CAND];
+  __shared__ int s_idx[8][IV_CAND];
+  const int w = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + w;
   const int lane = threadIdx.x & 31;
   if (row >= misc[2]) return;
   const int per = C >> 5;
@@ -45,6 +53,53 @@ gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C
 #pragma unroll
   for (int i = 0; i < 64; ++i)
     if (v[i] > best) { best = v[i]; bi = i; }
+  float M = best;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  // ---- threshold bisection: delta_lo passes fewer than 20 values, delta_hi more than IV_CAND
+  float d_lo = 0.f, d_hi = -1.f, delta = 8.f, tau = 0.f;
+  int cnt = 0, mine = 0;
+  bool ok = false;
+  for (int it = 0; it < 24 && !ok; ++it) {
+    tau = M - delta;
+    mine = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) mine += (v[i] >= tau) ? 1 : 0;
+    cnt = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (cnt < IV_NSEL) { d_lo = delta; delta = (d_hi > 0.f) ? 0.5f * (d_lo + d_hi) : 2.f * delta; }
+    else if (cnt > IV_CAND) { d_hi = delta; delta = 0.5f * (d_lo + d_hi); }
+    else ok = true;
+  }
+  if (ok) {
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    int pos = incl - mine;
+#pragma unroll
+    for (int i = 0; i < 64; ++i)
+      if (v[i] >= tau) { s_val[w][pos] = v[i]; s_idx[w][pos] = lane + 32 * i; ++pos; }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < IV_CAND / 32; ++h) {
+      const int me = lane + 32 * h;
+      if (me < cnt) {
+        const float a = s_val[w][me];
+        const int ai = s_idx[w][me];
+        int rank = 0;
+        for (int j = 0; j < cnt; ++j) {
+          const float o = s_val[w][j];
+          rank += (o > a || (o == a && s_idx[w][j] < ai)) ? 1 : 0;
+        }
+        if (rank < IV_NSEL) gsel[(size_t)row * IV_NSEL + rank] = ai;
+      }
+    }
+    return;
+  }
   for (int k = 0; k < IV_NSEL; ++k) {
     float wv = best;
     int wi = lane + 32 * bi;                      // component index
@@ -419,6 +474,7 @@ ivec_derive_u_kernel(const double *__restrict__ M, const double *__restrict__ si
 #define IV_BCHUNK 32
 
 // lin partials: grid (n_splits, ceil(B/32)); block = 4 utterance-groups x ceil(R/4) column-groups (R <= 512).
+static_assert(FB_DIM % 4 == 0, "ivec_lin_kernel walks the feature dimension four rows at a time");
 __global__ void __launch_bounds__(512)
 ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, const double *__restrict__ gamma, int B, int C,
                 int R, int n_splits, double *__restrict__ part, const int *__restrict__ done_flag) {
@@ -450,22 +506,30 @@ ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, 
     __syncthreads();
     if (!s_any || !active) continue;
     const float *col = sim32 + (size_t)c * FB_DIM * R + r0;
-    for (int d = 0; d < FB_DIM; ++d) {
-      float p[4];
-      if (r0 + 3 < R && (R & 3) == 0) {
-        const float4 q = *reinterpret_cast<const float4 *>(col + (size_t)d * R);
-        p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
-      } else {
+    const bool vec_ok = r0 + 3 < R && (R & 3) == 0;
+    // four parameter rows in flight per thread: the 236 MB stream is latency bound with one
+    for (int d0 = 0; d0 < FB_DIM; d0 += 4) {
+      float p[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = (r0 + i < R) ? col[(size_t)d * R + i] : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        if (vec_ok) {
+          const float4 q = __ldcs(reinterpret_cast<const float4 *>(col + (size_t)(d0 + u) * R));
+          p[u][0] = q.x; p[u][1] = q.y; p[u][2] = q.z; p[u][3] = q.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) p[u][i] = (r0 + i < R) ? col[(size_t)(d0 + u) * R + i] : 0.f;
+        }
       }
-      const double2 *xr = reinterpret_cast<const double2 *>(&s_x[d][ug * 8]);
-      const double2 x01 = xr[0], x23 = xr[1], x45 = xr[2], x67 = xr[3];
-      const double x[8] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y, x67.x, x67.y};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int u = 0; u < 4; ++u) {
+        const double2 *xr = reinterpret_cast<const double2 *>(&s_x[d0 + u][ug * 8]);
+        const double2 x01 = xr[0], x23 = xr[1], x45 = xr[2], x67 = xr[3];
+        const double x[8] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y, x67.x, x67.y};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] += (double)p[i] * x[j];
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] += (double)p[u][i] * x[j];
+      }
     }
   }
   if (active)
