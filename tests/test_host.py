@@ -195,3 +195,26 @@ def test_sharded_gradient_allreduce_matches_single_process_gloo():
     assert np.allclose(red[:N] / S / 1e-3, grad[:, 0], rtol=1e-12, atol=1e-12)
     assert red[N] == adver_loss[0] and np.isclose(red[N + 1:N + 1 + S].mean(), final_loss, rtol=1e-14)
     assert np.array_equal(red[N + S + 1:], score)
+
+
+def test_set_threshold_matches_reference_search():
+    """fakebob_b200.evaluate.set_threshold against a direct restatement of the loop at test.py:46-71."""
+    from fakebob_b200.evaluate import set_threshold
+
+    def slow(score_target, score_untarget):
+        best, best_d, best_far, best_frr = 0.0, np.inf, 0.0, 0.0
+        for thr in score_target:
+            frr = np.count_nonzero(score_target < thr) * 100 / score_target.size
+            far = np.count_nonzero(score_untarget >= thr) * 100 / score_untarget.size
+            if abs(frr - far) < best_d:
+                best, best_d, best_far, best_frr = thr, abs(frr - far), far, frr
+        return best, best_frr, best_far
+
+    r = np.random.default_rng(5)
+    for n_t, n_u in ((1, 1), (7, 3), (50, 200), (200, 50)):
+        st = r.normal(1.0, 1.0, n_t)
+        su = r.normal(-1.0, 1.0, n_u)
+        st[::5] = np.round(st[::5], 1)                      # ties
+        su[::4] = np.round(su[::4], 1)
+        assert set_threshold(st, su) == pytest.approx(slow(st, su), abs=0)
+    assert set_threshold([0.5, 0.5, 2.0], [0.5, -1.0])[0] == 0.5
