@@ -31,6 +31,10 @@ N_SAMPLES = 80000
 N_SPEAKERS = 5
 N_MIX = 2048
 EPSILON = 0.002
+# dram__bytes_read.sum + dram__bytes_write.sum of gmm_umma_kernel at this workload, one `ncu --set full` capture
+# (profiles/r01_ncu_iter_v5_summary.txt): 19.53 MB read (the fp16 operand image written by feats_kernel; the 4.5 MB W image
+# stays in L2), ~0 written (partials stay in L2).  The kernel is tensor-pipe bound; traffic is reported for completeness.
+GMM_DRAM_BYTES_PER_LAUNCH = 19533056
 WORKLOAD = "C2: gmm_OSI untargeted, UBM+5 spk x 2048 mix, samples_per_draw=50, 5 s @ 16 kHz, eps=0.002"
 
 
@@ -405,7 +409,8 @@ def main():
                                "how": "one FakeBob.attack(audio_host) call of %d iterations, default iters_per_launch, host wall clock" % K},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "gmm_umma_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": GMM_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_unit": "bytes/launch (dram read + write, profiles/r01_ncu_iter_v5_summary.txt)", "peak_source": peak_src,
                          "algorithmic_flops_per_launch": flops, "kernel_ms": gmm_ms_avg,
                          "executed_flops_per_launch": 3.0 * flops,
                          "note": "algorithmic = 2*rows*C*(2D) per model (Kaldi's two sgemv per frame); the kernel executes 3x that "
