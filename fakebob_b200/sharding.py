@@ -15,3 +15,30 @@ def pair_range(pairs_total, rank, world):
 def global_column(pairs_total, pair, sign):
     """Column of `loss` / `noise` in the reference's layout [clean | +pairs | -pairs]."""
     return 1 + pair if sign > 0 else 1 + pairs_total + pair
+
+
+def utterance_range(n_utterances, rank, world):
+    """Independent attacks shard by utterance, no collective (BASELINE.json configs[4]: a batch of concurrent attack
+    utterances over the GPUs of one box): rank r attacks utterances [floor(U r / W), floor(U (r+1) / W))."""
+    return (n_utterances * rank) // world, (n_utterances * (rank + 1)) // world
+
+
+def attack_many(make_attacker, audios, rank=0, world=1, **attack_kwargs):
+    """Run one independent ``FakeBob.attack`` per utterance of this rank's shard.
+
+    make_attacker() -> a FakeBob bound to this rank's device (built once, reused for every utterance);
+    audios: sequence of 1-D float audios; attack_kwargs: forwarded to ``attack`` (threshold=, target=, ...; a callable value
+    is called with the utterance index).  Returns {utterance index: (adver int16 (N,1), success flag)} for the shard; the
+    caller gathers the dicts (e.g. ``torch.distributed.all_gather_object``) -- the attacks themselves never communicate."""
+    lo, hi = utterance_range(len(audios), rank, world)
+    fb = make_attacker()
+    base_seed = fb.seed
+    out = {}
+    for u in range(lo, hi):
+        # one Philox stream per utterance, a function of (seed, utterance index) only: the result of an attack does not
+        # depend on how the utterances were sharded
+        fb.seed = (base_seed + 0x9E3779B97F4A7C15 * (u + 1)) % (1 << 62)
+        fb.draws = 0
+        kw = {k: (v(u) if callable(v) else v) for k, v in attack_kwargs.items()}
+        out[u] = fb.attack(audios[u], kw.pop("checkpoint_path", None), **kw)
+    return out
