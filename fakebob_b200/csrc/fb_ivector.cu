@@ -131,6 +131,7 @@ gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C
 // inv_covars are packed lower-triangular row-major (Kaldi SpMatrix), D = 72 -> 2628 entries.
 // ------------------------------------------------------------------------------------------------
 #define IV_PACKED (FB_DIM * (FB_DIM + 1) / 2)
+#define IV_STATS_SPLIT 2       // CTAs per utterance in ivec_stats_kernel (component ranges); ~144 KB smem each: one wave at B = 51
 
 __global__ void __launch_bounds__(256)
 fgmm_post_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, const float *__restrict__ gconsts,
@@ -369,6 +370,8 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
   float *lq = lp + max_pairs;                                 // [max_pairs] sorted
   __shared__ int s_scan[256];
   const int b = blockIdx.x;
+  // blockIdx.y splits the components: a CTA buckets and accumulates only the pairs of its component range
+  const int cq0 = (int)((long long)C * blockIdx.y / gridDim.y), cq1 = (int)((long long)C * (blockIdx.y + 1) / gridDim.y);
   const int r0 = row_off[b], Tv = row_off[b + 1] - r0;
   const int tid = threadIdx.x;
   if (Tv * IV_NSEL > max_pairs) {
@@ -377,8 +380,10 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
   }
   for (int c = tid; c < C; c += blockDim.x) { cnt[c] = 0; cur[c] = 0; }
   __syncthreads();
-  for (int i = tid; i < Tv * IV_NSEL; i += blockDim.x)
-    if (post[(size_t)r0 * IV_NSEL + i] != 0.f) atomicAdd(&cnt[gsel[(size_t)r0 * IV_NSEL + i]], 1);
+  for (int i = tid; i < Tv * IV_NSEL; i += blockDim.x) {
+    const int c = gsel[(size_t)r0 * IV_NSEL + i];
+    if (c >= cq0 && c < cq1 && post[(size_t)r0 * IV_NSEL + i] != 0.f) atomicAdd(&cnt[c], 1);
+  }
   __syncthreads();
   // exclusive scan of cnt (C <= 2048: 8 per thread)
   const int per = (C + 255) / 256;
@@ -397,8 +402,8 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
   __syncthreads();
   for (int i = tid; i < Tv * IV_NSEL; i += blockDim.x) {
     const float p = post[(size_t)r0 * IV_NSEL + i];
-    if (p != 0.f) {
-      const int c = gsel[(size_t)r0 * IV_NSEL + i];
+    const int c = gsel[(size_t)r0 * IV_NSEL + i];
+    if (p != 0.f && c >= cq0 && c < cq1) {
       const int pos = off[c] + atomicAdd(&cur[c], 1);
       lt[pos] = (unsigned short)(i / IV_NSEL);
       lp[pos] = p;
@@ -406,7 +411,7 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
   }
   __syncthreads();
   const int w = tid >> 5, lane = tid & 31;
-  for (int c = w; c < C; c += 8) {
+  for (int c = cq0 + w; c < cq1; c += 8) {
     const int n = cnt[c], o = off[c];
     // rank sort by frame index (frame indices within a bucket are distinct)
     for (int i = lane; i < n; i += 32) {
@@ -1214,7 +1219,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
     FB_CUDA(cudaFuncSetAttribute(ivec_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
-  ivec_stats_kernel<<<B, 256, smem_stats, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->post.p, ctx->row_off.p, v->C, max_pairs,
+  ivec_stats_kernel<<<dim3(B, IV_STATS_SPLIT), 256, smem_stats, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->post.p, ctx->row_off.p, v->C, max_pairs,
                                                          v->gamma.p, v->Xs.p, ctx->misc.p + 1, done_flag);
   fb_prof_mark(ctx, 10);
   const int bch = fb_div_up(B, IV_BCHUNK);
