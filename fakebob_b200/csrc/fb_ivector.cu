@@ -15,6 +15,7 @@
 // The derived extractor matrices (Sigma^-1 M, U) are computed ONCE at load on the device (Kaldi recomputes them on every
 // ivector-extract invocation).
 #include "fb_common.cuh"
+#include <cooperative_groups.h>
 #include "fb_ivector.cuh"
 #include <math.h>
 #include <string.h>
@@ -642,9 +643,13 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
 //   L21 = A21 L11^-T one thread per row, the row in registers, L11 broadcast from shared memory
 //   trailing update  warp tiles of 8 rows x 128 columns (lane owns columns l, l+32, l+64, l+96: conflict-free panel reads,
 //                    coalesced global read-modify-write), 32 accumulators per lane
+// A thread-block cluster of IV_SOLVE_CLUSTER CTAs works on one utterance: every CTA factors the (small) panel redundantly
+// -- identical arithmetic, identical results -- and takes every IV_SOLVE_CLUSTER-th tile of the trailing update; a
+// cluster barrier (release / acquire) per block column makes the updates visible to the partner.
 // ------------------------------------------------------------------------------------------------
 #define IV_NB 32
 #define IV_PSTRIDE 33      // padded panel row stride (doubles): consecutive rows map to different banks
+#define IV_SOLVE_CLUSTER 2 // CTAs (SMs) per utterance: at B = 51 one CTA per utterance would leave 97 of 148 SMs idle
 
 __global__ void __launch_bounds__(512)
 ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ lin_part, int n_splits, int B, int R, int n_packed,
@@ -666,7 +671,9 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   __shared__ double s_invd[IV_NB];
   __shared__ double s_blk[IV_NB];
   __shared__ int s_fail;
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int b = blockIdx.x / csize, tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   double *A = Awork + (size_t)b * R * R;
   if (tid == 0) s_fail = 0;
@@ -745,7 +752,10 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
     }
     __syncthreads();
     IV_LAP(2);
-    if (s_fail) { if (tid == 0) atomicExch(err, 3); return; }
+    if (s_fail) {                                    // both CTAs of the cluster take this exit in the same block column
+      if (tid == 0) atomicExch(err, 3);
+      return;
+    }
     // ---- rows below the diagonal block and the rhs row: x = a L11^-T, the row in registers
     for (int i = nbk + tid; i <= rows; i += nt) {
       double *row = panel + i * IV_PSTRIDE;
@@ -780,11 +790,12 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
         rhs[k0 + j] = v;
       }
     }
-    // ---- write the factored block column back
-    for (int idx = tid; idx < rows * IV_NB; idx += nt) {
-      const int i = idx >> 5, j = idx & 31;
-      if (j < nbk && j <= i) A[(size_t)(k0 + i) * R + k0 + j] = panel[i * IV_PSTRIDE + j];
-    }
+    // ---- write the factored block column back (rank 0; the partner holds the same values)
+    if (crank == 0)
+      for (int idx = tid; idx < rows * IV_NB; idx += nt) {
+        const int i = idx >> 5, j = idx & 31;
+        if (j < nbk && j <= i) A[(size_t)(k0 + i) * R + k0 + j] = panel[i * IV_PSTRIDE + j];
+      }
     IV_LAP(4);
     // ---- trailing update A22 -= L21 L21^T on the lower triangle: warp tiles of 8 rows x 128 columns
     const int rem = rows - nbk;
@@ -792,7 +803,7 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
       const int nrb = (rem + 7) >> 3, ncb = (rem + 127) >> 7;
       int n_items = 0;
       for (int cb = 0; cb < ncb; ++cb) n_items += nrb - 16 * cb;
-      for (int it = warp; it < n_items; it += nw) {
+      for (int it = warp * csize + crank; it < n_items; it += nw * csize) {
         int cb = 0, rb = it;
         while (rb >= nrb - 16 * cb) { rb -= nrb - 16 * cb; ++cb; }
         rb += 16 * cb;
@@ -832,7 +843,8 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
           }
       }
     }
-    __syncthreads();
+    if (csize > 1) cluster.sync();                   // the partner's trailing-update tiles are visible (release / acquire)
+    else __syncthreads();
     IV_LAP(5);
   }
   // rhs now holds y = L^-1 b.  Backward substitution L^T w = y, blocked from the last block.
@@ -870,7 +882,8 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
     printf("solve tid %d clk: init %lld load %lld diag %lld l21 %lld rhs+wb %lld trailing %lld backsub %lld\n", tid, st[0], st[1], st[2], st[3],
            st[4], st[5], st[6]);
 #endif
-  for (int r = tid; r < R; r += nt) ivec[(size_t)b * R + r] = (float)(rhs[r] - ((r == 0) ? prior_offset : 0.0));
+  if (crank == 0)
+    for (int r = tid; r < R; r += nt) ivec[(size_t)b * R + r] = (float)(rhs[r] - ((r == 0) ? prior_offset : 0.0));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1236,9 +1249,22 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
     FB_CUDA(cudaFuncSetAttribute(ivec_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_solve = true;
   }
-  ivec_solve_kernel<<<B, 512, smem_solve, ctx->stream>>>(v->quad.p, v->lin_part.p, v->n_splits, B, v->R, v->n_packed,
-                                                                        v->prior_offset, v->Awork.p, v->ivec.p, ctx->misc.p + 1,
-                                                                        done_flag);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * IV_SOLVE_CLUSTER);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem_solve;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = IV_SOLVE_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FB_CUDA(cudaLaunchKernelEx(&cfg, ivec_solve_kernel, (const double *)v->quad.p, (const double *)v->lin_part.p, v->n_splits, B, v->R,
+                               v->n_packed, v->prior_offset, v->Awork.p, v->ivec.p, ctx->misc.p + 1, done_flag));
+  }
   fb_prof_mark(ctx, 13);
   ctx->launches += 6;
   if (with_plda) {
