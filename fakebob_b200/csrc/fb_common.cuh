@@ -166,4 +166,11 @@ int fb_run_frontend(fb_ctx *ctx);             // mfcc -> vad_scan -> feats (wave
 int fb_run_gmm(fb_ctx *ctx);                  // gmm -> reduce into avg_ll
 void fb_prof_mark(fb_ctx *ctx, int tag);
 // helpers
+// cudaFuncSetAttribute is per device: one flag per device ordinal (a process may hold contexts on several GPUs)
+static inline bool fb_once_per_device(unsigned long long &mask, int device) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
 static inline int fb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

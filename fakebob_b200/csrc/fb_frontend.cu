@@ -622,10 +622,9 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   fb_prof_mark(ctx, 2);
   const size_t smem = fb_feats_smem_bytes(ctx->max_frames);
   const int use_smem = smem <= FB_FEATS_SMEM_MAX;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_mask = 0;
+  if (fb_once_per_device(configured_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(feats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_FEATS_SMEM_MAX));
-    configured = true;
   }
   feats_kernel<<<dim3(9, B), FEATS_THREADS, use_smem ? smem : 0, ctx->stream>>>(
       ctx->mfcc.p, ctx->frame_off.p, ctx->vrank.p, ctx->row_off.p, ctx->tables_dev, ctx->a_img.p,

@@ -820,12 +820,11 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
   ctx->frame_ll.release();
   ctx->avg_ll.release();
   ctx->batch_tag = -1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set_mask = 0;
+  if (fb_once_per_device(attr_set_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
     FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
     FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
-    attr_set = true;
   }
   return FB_OK;
 }

@@ -1227,10 +1227,9 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
                  (int)((220 * 1024 - 3 * v->C * 4) / (IV_NSEL * 12)));
     return FB_ERR_UNSUPPORTED;
   }
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;
+  if (fb_once_per_device(attr_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(ivec_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr = true;
   }
   ivec_stats_kernel<<<dim3(B, IV_STATS_SPLIT), 256, smem_stats, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->post.p, ctx->row_off.p, v->C, max_pairs,
                                                          v->gamma.p, v->Xs.p, ctx->misc.p + 1, done_flag);
@@ -1244,10 +1243,9 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
                                                                                    v->quad.p, done_flag);
   fb_prof_mark(ctx, 12);
   const size_t smem_solve = (2 * (size_t)v->R + ((size_t)v->R + 2) * IV_PSTRIDE) * sizeof(double);
-  static bool attr_solve = false;
-  if (!attr_solve) {
+  static unsigned long long attr_solve_mask = 0;
+  if (fb_once_per_device(attr_solve_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(ivec_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_solve = true;
   }
   {
     cudaLaunchConfig_t cfg = {};
