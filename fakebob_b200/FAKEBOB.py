@@ -103,8 +103,10 @@ class FakeBob(object):
         self.true = true
         self.target = target
         n = audio.shape[0]
+        t_init = time.time()
         eng = self._nes_init(audio, self.max_iter)
         t_start = time.time()
+        self.poll_times = [t_start - t_init]         # seconds: fb_nes_init, then one entry per polled batch of iterations
         done, stopped, printed = 0, False, 0
         chunk = 1 if self.rng == "numpy" else self.iters_per_launch
         while not stopped and done < self.max_iter:
@@ -112,8 +114,10 @@ class FakeBob(object):
             noise = None
             if self.rng == "numpy":
                 noise = np.stack([self._host_noise(n) for _ in range(k)])
+            t_poll = time.time()
             eng.nes_run(k, noise)
             done, stopped = eng.nes_status()
+            self.poll_times.append(time.time() - t_poll)
             if self.verbose:
                 rows = eng.nes_log(done)
                 for it in range(printed, done):

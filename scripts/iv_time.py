@@ -42,12 +42,13 @@ print("score 51 x 5 s: %.2f ms / call; scores[:3]=%s" % ((time.time() - t0) / 3 
 audio = synth.synth_utterance(0, 0, 80000)
 fb = FakeBob("SV", "untargeted", model, max_iter=60, samples_per_draw=50, seed=1, verbose=False)
 fb.attack(audio, None, threshold=1e6)
-for rep in range(3):                                # wall clock of whole attack() calls: includes fb_nes_init, graph capture, polling
+for rep in range(6):                                # wall clock of whole attack() calls: includes fb_nes_init, graph capture, polling
     fb = FakeBob("SV", "untargeted", model, max_iter=100, samples_per_draw=50, seed=1, verbose=False)
     t0 = time.time()
     fb.attack(audio, None, threshold=1e6)
     dt = time.time() - t0
     print("NES iv_SV S=50: %d iters in %.3fs -> %.1f it/s (%.3f ms/iter)" % (fb.iters_done, dt, fb.iters_done / dt, dt / fb.iters_done * 1e3), flush=True)
+    print("   init + per-poll seconds:", [round(x, 3) for x in fb.poll_times], flush=True)
 e = model._engine
 e.profile(True)
 fb = FakeBob("SV", "untargeted", model, max_iter=20, samples_per_draw=50, seed=1, verbose=False)
