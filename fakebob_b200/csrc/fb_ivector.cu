@@ -548,20 +548,57 @@ ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, 
       }
 }
 
+// Active components of a 32-utterance chunk: c is active when gamma[b][c] != 0 for some utterance of the chunk (top-20
+// selection + posterior pruning leave ~18 % of the components at C3).  One CTA per chunk; ordered (ascending) compaction so
+// that consumers accumulate in the same order as a plain loop over c.  list[0] = count, list[1..] = components.
+__global__ void __launch_bounds__(1024)
+ivec_active_kernel(const double *__restrict__ gamma, int B, int C, int *__restrict__ act_list, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int b0 = blockIdx.x * IV_BCHUNK;
+  const int nb = min(IV_BCHUNK, B - b0);
+  int *list = act_list + (size_t)blockIdx.x * (C + 1);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    bool act = false;
+    if (c < C)
+      for (int i = 0; i < nb; ++i) act |= gamma[(size_t)(b0 + i) * C + c] != 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int k = 0; k < w; ++k) before += s_warp[k];
+    if (act) list[1 + before + __popc(bal & ((1u << lane) - 1u))] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += s_warp[k];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) list[0] = s_base;
+}
+
 // quad: grid (ceil(n_packed / 256), ceil(B/32)); block 256 = 4 utterance-groups x 64 column-groups of 4 packed entries.
-// The kernel streams U (C x n_packed fp32, 657 MB at C = 2048, R = 400) from HBM with one 16-byte load per thread and
-// component, so it is latency bound unless several loads are in flight: the active components of a 64-component chunk are
-// compacted into a list and processed four at a time with their loads issued up front.
+// The kernel streams the ACTIVE rows of U (C x n_packed fp32, 657 MB at C = 2048, R = 400; ~120 MB active at C3) with one
+// 16-byte load per thread and component, so it is latency bound unless several loads are in flight and the per-chunk
+// bookkeeping is rare: it walks the compacted active list 64 components at a time (their gammas gathered into shared
+// memory once per chunk) and issues the loads of four components before the first FMA.
 __global__ void __launch_bounds__(256, 2)
-ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, int B, int C, int n_packed,
-                 double *__restrict__ quad, const int *__restrict__ done_flag) {
+ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, const int *__restrict__ act_list, int B, int C,
+                 int n_packed, double *__restrict__ quad, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
   __shared__ __align__(16) double s_g[64][IV_BCHUNK];
-  __shared__ int s_any[64];
-  __shared__ int s_list[64 + 4];
-  __shared__ int s_n;
+  __shared__ int s_c[64];
   const int b0 = blockIdx.y * IV_BCHUNK;
   const int nb = min(IV_BCHUNK, B - b0);
+  const int *list = act_list + (size_t)blockIdx.y * (C + 1);
+  const int n_act = list[0];
   const int ug = threadIdx.x >> 6, cg = threadIdx.x & 63;
   const int e0 = blockIdx.x * 256 + cg * 4;
   const bool vec_ok = (n_packed & 3) == 0 && e0 + 3 < n_packed;
@@ -589,40 +626,26 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] += (double)p[i] * gv[j];
   };
-  for (int cb = 0; cb < C; cb += 64) {
+  for (int a0 = 0; a0 < n_act; a0 += 64) {
+    const int n = min(64, n_act - a0);
     __syncthreads();
-    if (threadIdx.x < 64) s_any[threadIdx.x] = 0;
+    if (threadIdx.x < 64) s_c[threadIdx.x] = (threadIdx.x < n) ? list[1 + a0 + threadIdx.x] : 0;
     __syncthreads();
     for (int idx = threadIdx.x; idx < 64 * IV_BCHUNK; idx += blockDim.x) {
       const int k = idx / IV_BCHUNK, i = idx - k * IV_BCHUNK;
-      const double g = (i < nb && cb + k < C) ? gamma[(size_t)(b0 + i) * C + cb + k] : 0.0;
-      s_g[k][i] = g;
-      if (g != 0.0) s_any[k] = 1;
+      s_g[k][i] = (i < nb && k < n) ? gamma[(size_t)(b0 + i) * C + s_c[k]] : 0.0;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {                       // ordered compaction of the active components (ascending k, like the plain loop)
-      const int lane = threadIdx.x;
-      const unsigned m0 = __ballot_sync(0xffffffffu, s_any[lane] != 0);
-      const unsigned m1 = __ballot_sync(0xffffffffu, s_any[32 + lane] != 0);
-      const unsigned below = (1u << lane) - 1u;
-      if (m0 & (1u << lane)) s_list[__popc(m0 & below)] = lane;
-      if (m1 & (1u << lane)) s_list[__popc(m0) + __popc(m1 & below)] = 32 + lane;
-      if (lane == 0) s_n = __popc(m0) + __popc(m1);
-    }
-    __syncthreads();
-    const int n = s_n;
     int i = 0;
     for (; i + 4 <= n; i += 4) {
-      const int k0 = s_list[i], k1 = s_list[i + 1], k2 = s_list[i + 2], k3 = s_list[i + 3];
       float p0[4], p1[4], p2[4], p3[4];
-      load_row(cb + k0, p0); load_row(cb + k1, p1); load_row(cb + k2, p2); load_row(cb + k3, p3);
-      fma_row(k0, p0); fma_row(k1, p1); fma_row(k2, p2); fma_row(k3, p3);
+      load_row(s_c[i], p0); load_row(s_c[i + 1], p1); load_row(s_c[i + 2], p2); load_row(s_c[i + 3], p3);
+      fma_row(i, p0); fma_row(i + 1, p1); fma_row(i + 2, p2); fma_row(i + 3, p3);
     }
     for (; i < n; ++i) {
-      const int k = s_list[i];
       float p[4];
-      load_row(cb + k, p);
-      fma_row(k, p);
+      load_row(s_c[i], p);
+      fma_row(i, p);
     }
   }
 #pragma unroll
@@ -981,7 +1004,7 @@ static void iv_release(FbIvector *v) {
   v->gconsts.release(); v->means_invcovars.release(); v->inv_covars.release(); v->rc_table.release();
   v->sim32.release(); v->U.release(); v->mean_vec.release(); v->lda.release(); v->plda_T.release();
   v->plda_off.release(); v->psi.release(); v->u_train.release();
-  v->ll.release(); v->gsel.release(); v->post.release(); v->gamma.release(); v->Xs.release(); v->lin_part.release();
+  v->ll.release(); v->gsel.release(); v->post.release(); v->act_list.release(); v->gamma.release(); v->Xs.release(); v->lin_part.release();
   v->quad.release(); v->Awork.release(); v->ivec.release(); v->scores.release();
   delete v;
 }
@@ -1189,6 +1212,7 @@ int fb_ivector_reserve(fb_ctx *ctx) {
   v->n_splits = ctx->num_sms < v->C ? ctx->num_sms : v->C;
   if ((rc = v->lin_part.ensure((size_t)v->n_splits * B * v->R))) return rc;
   if ((rc = v->quad.ensure((size_t)B * v->n_packed))) return rc;
+  if ((rc = v->act_list.ensure((size_t)fb_div_up(B, IV_BCHUNK) * (v->C + 1)))) return rc;
   if ((rc = v->Awork.ensure((size_t)B * v->R * v->R))) return rc;
   if ((rc = v->ivec.ensure((size_t)B * v->R))) return rc;
   if ((rc = v->scores.ensure((size_t)B * (v->K > 0 ? v->K : 1)))) return rc;
@@ -1239,8 +1263,9 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   ivec_lin_kernel<<<dim3(v->n_splits, bch), lin_threads, 0, ctx->stream>>>(v->sim32.p, v->Xs.p, v->gamma.p, B, v->C, v->R,
                                                                           v->n_splits, v->lin_part.p, done_flag);
   fb_prof_mark(ctx, 11);
-  ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, B, v->C, v->n_packed,
-                                                                                   v->quad.p, done_flag);
+  ivec_active_kernel<<<bch, 1024, 0, ctx->stream>>>(v->gamma.p, B, v->C, v->act_list.p, done_flag);
+  ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, v->act_list.p, B, v->C,
+                                                                                   v->n_packed, v->quad.p, done_flag);
   fb_prof_mark(ctx, 12);
   const size_t smem_solve = (2 * (size_t)v->R + ((size_t)v->R + 2) * IV_PSTRIDE) * sizeof(double);
   static unsigned long long attr_solve_mask = 0;
@@ -1264,7 +1289,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
                                v->n_packed, v->prior_offset, v->Awork.p, v->ivec.p, ctx->misc.p + 1, done_flag));
   }
   fb_prof_mark(ctx, 13);
-  ctx->launches += 6;
+  ctx->launches += 7;
   if (with_plda) {
     const size_t smem_plda = (size_t)v->L * sizeof(double) + (size_t)(v->R + v->L) * sizeof(float) + 16;
     plda_kernel<<<B, 256, smem_plda, ctx->stream>>>(v->ivec.p, v->mean_vec.p, v->lda.p, v->lda_cols, v->plda_T.p, v->plda_off.p,

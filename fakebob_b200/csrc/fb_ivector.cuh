@@ -22,6 +22,7 @@ struct FbIvector {
   DevBuf<float> post;                                       // [rows_cap][20]
   DevBuf<double> gamma, Xs, lin_part, quad, Awork, scores;
   DevBuf<float> ivec;
+  DevBuf<int> act_list;                                     // [ceil(B/32)][C + 1]: [0] = count, then the active components, ascending
 };
 
 void fb_ivector_destroy(fb_ctx *ctx);
