@@ -482,15 +482,17 @@ ivec_derive_u_kernel(const double *__restrict__ M, const double *__restrict__ si
 // lin partials: grid (n_splits, ceil(B/32)); block = 4 utterance-groups x ceil(R/4) column-groups (R <= 512).
 static_assert(FB_DIM % 4 == 0, "ivec_lin_kernel walks the feature dimension four rows at a time");
 __global__ void __launch_bounds__(512)
-ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, const double *__restrict__ gamma, int B, int C,
+ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, const int *__restrict__ act_list, int B, int C,
                 int R, int n_splits, double *__restrict__ part, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
   __shared__ __align__(16) double s_x[FB_DIM][IV_BCHUNK];
-  __shared__ int s_any;
   const int split = blockIdx.x;
   const int b0 = blockIdx.y * IV_BCHUNK;
   const int nb = min(IV_BCHUNK, B - b0);
-  const int c0 = (int)((long long)C * split / n_splits), c1 = (int)((long long)C * (split + 1) / n_splits);
+  // the ACTIVE components of this utterance chunk (ivec_active_kernel), split evenly over the CTAs of the row
+  const int *list = act_list + (size_t)blockIdx.y * (C + 1);
+  const int n_act = list[0];
+  const int a_lo = (int)((long long)n_act * split / n_splits), a_hi = (int)((long long)n_act * (split + 1) / n_splits);
   const int ncg = (R + 3) / 4;
   const int ug = threadIdx.x / ncg, cg = threadIdx.x - ug * ncg;      // utterance group 0..3, column group
   const bool active = ug < 4;
@@ -500,17 +502,15 @@ ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-  for (int c = c0; c < c1; ++c) {
+  for (int ai = a_lo; ai < a_hi; ++ai) {
+    const int c = list[1 + ai];
     __syncthreads();
-    if (threadIdx.x == 0) s_any = 0;
-    __syncthreads();
-    if (threadIdx.x < nb && gamma[(size_t)(b0 + threadIdx.x) * C + c] != 0.0) s_any = 1;
     for (int idx = threadIdx.x; idx < FB_DIM * IV_BCHUNK; idx += blockDim.x) {
       const int d = idx / IV_BCHUNK, i = idx - d * IV_BCHUNK;
       s_x[d][i] = (i < nb) ? Xs[((size_t)(b0 + i) * C + c) * FB_DIM + d] : 0.0;
     }
     __syncthreads();
-    if (!s_any || !active) continue;
+    if (!active) continue;
     const float *col = sim32 + (size_t)c * FB_DIM * R + r0;
     const bool vec_ok = r0 + 3 < R && (R & 3) == 0;
     // four parameter rows in flight per thread: the 236 MB stream is latency bound with one
@@ -1260,10 +1260,10 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   fb_prof_mark(ctx, 10);
   const int bch = fb_div_up(B, IV_BCHUNK);
   const int lin_threads = ((4 * ((v->R + 3) / 4) + 31) / 32) * 32;
-  ivec_lin_kernel<<<dim3(v->n_splits, bch), lin_threads, 0, ctx->stream>>>(v->sim32.p, v->Xs.p, v->gamma.p, B, v->C, v->R,
+  ivec_active_kernel<<<bch, 1024, 0, ctx->stream>>>(v->gamma.p, B, v->C, v->act_list.p, done_flag);
+  ivec_lin_kernel<<<dim3(v->n_splits, bch), lin_threads, 0, ctx->stream>>>(v->sim32.p, v->Xs.p, v->act_list.p, B, v->C, v->R,
                                                                           v->n_splits, v->lin_part.p, done_flag);
   fb_prof_mark(ctx, 11);
-  ivec_active_kernel<<<bch, 1024, 0, ctx->stream>>>(v->gamma.p, B, v->C, v->act_list.p, done_flag);
   ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, v->act_list.p, B, v->C,
                                                                                    v->n_packed, v->quad.p, done_flag);
   fb_prof_mark(ctx, 12);
