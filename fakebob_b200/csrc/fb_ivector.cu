@@ -132,6 +132,7 @@ gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C
 // inv_covars are packed lower-triangular row-major (Kaldi SpMatrix), D = 72 -> 2628 entries.
 // ------------------------------------------------------------------------------------------------
 #define IV_PACKED (FB_DIM * (FB_DIM + 1) / 2)
+#define IV_STATS_THREADS 1024  // the per-component accumulation is a chain of L2 round trips: many warps per CTA
 #define IV_STATS_SPLIT 2       // CTAs per utterance in ivec_stats_kernel (component ranges); ~144 KB smem each: one wave at B = 51
 
 __global__ void __launch_bounds__(256)
@@ -356,7 +357,7 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
 // Pairs are bucketed by component in shared memory, each bucket is put in frame order (rank sort), then one warp
 // per component accumulates sequentially -- the same order as Kaldi's per-frame AccStats, deterministic.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(IV_STATS_THREADS)
 ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, const float *__restrict__ post,
                   const int *__restrict__ row_off, int C, int max_pairs, double *__restrict__ gamma,
                   double *__restrict__ Xs, int *__restrict__ err, const int *__restrict__ done_flag) {
@@ -386,20 +387,24 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
     if (c >= cq0 && c < cq1 && post[(size_t)r0 * IV_NSEL + i] != 0.f) atomicAdd(&cnt[c], 1);
   }
   __syncthreads();
-  // exclusive scan of cnt (C <= 2048: 8 per thread)
+  // exclusive scan of cnt by the first 256 threads (C <= 2048: 8 per thread); the block may be larger
   const int per = (C + 255) / 256;
-  int local = 0;
-  for (int k = 0; k < per; ++k) { const int c = tid * per + k; if (c < C) local += cnt[c]; }
-  s_scan[tid] = local;
+  if (tid < 256) {
+    int local = 0;
+    for (int k = 0; k < per; ++k) { const int c = tid * per + k; if (c < C) local += cnt[c]; }
+    s_scan[tid] = local;
+  }
   __syncthreads();
   if (tid == 0) {
     int run = 0;
     for (int i = 0; i < 256; ++i) { const int t = s_scan[i]; s_scan[i] = run; run += t; }
   }
   __syncthreads();
-  int run = s_scan[tid];
-  for (int k = 0; k < per; ++k) { const int c = tid * per + k; if (c < C) { off[c] = run; run += cnt[c]; } }
-  if (tid == 255) off[C] = run;
+  if (tid < 256) {
+    int run = s_scan[tid];
+    for (int k = 0; k < per; ++k) { const int c = tid * per + k; if (c < C) { off[c] = run; run += cnt[c]; } }
+    if (tid == 255) off[C] = run;
+  }
   __syncthreads();
   for (int i = tid; i < Tv * IV_NSEL; i += blockDim.x) {
     const float p = post[(size_t)r0 * IV_NSEL + i];
@@ -411,8 +416,8 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
     }
   }
   __syncthreads();
-  const int w = tid >> 5, lane = tid & 31;
-  for (int c = cq0 + w; c < cq1; c += 8) {
+  const int w = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
+  for (int c = cq0 + w; c < cq1; c += n_warps) {
     const int n = cnt[c], o = off[c];
     // rank sort by frame index (frame indices within a bucket are distinct)
     for (int i = lane; i < n; i += 32) {
@@ -1255,7 +1260,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   if (fb_once_per_device(attr_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(ivec_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   }
-  ivec_stats_kernel<<<dim3(B, IV_STATS_SPLIT), 256, smem_stats, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->post.p, ctx->row_off.p, v->C, max_pairs,
+  ivec_stats_kernel<<<dim3(B, IV_STATS_SPLIT), IV_STATS_THREADS, smem_stats, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->post.p, ctx->row_off.p, v->C, max_pairs,
                                                          v->gamma.p, v->Xs.p, ctx->misc.p + 1, done_flag);
   fb_prof_mark(ctx, 10);
   const int bch = fb_div_up(B, IV_BCHUNK);
