@@ -218,3 +218,90 @@ def test_set_threshold_matches_reference_search():
         su[::4] = np.round(su[::4], 1)
         assert set_threshold(st, su) == pytest.approx(slow(st, su), abs=0)
     assert set_threshold([0.5, 0.5, 2.0], [0.5, -1.0])[0] == 0.5
+
+
+def test_evaluation_helpers_with_stub_scorers():
+    """csi_accuracy / sv_error_rates / osi_error_rates (test.py sections) on scorers with known scores."""
+    from fakebob_b200 import evaluate as ev
+
+    class StubCsi:
+        spk_ids = ["a", "b", "c"]
+
+        def make_decisions(self, audios, **kw):
+            return [int(np.argmax(a[:3])) for a in audios], None
+
+    audios = [np.array([0.1, 0.9, 0.0]), np.array([0.7, 0.2, 0.1]), np.array([0.1, 0.2, 0.9]), np.array([0.5, 0.4, 0.1])]
+    assert ev.csi_accuracy(StubCsi(), audios, [1, 0, 2, 1]) == 75.0
+
+    class StubSv:
+        threshold = 0.0
+
+        def score(self, audios, **kw):
+            return np.array([float(a[0]) for a in audios])
+
+    sv = StubSv()
+    tgt = [np.array([s]) for s in (2.0, 1.5, 0.4, 3.0)]
+    imp = [np.array([s]) for s in (0.5, -1.0, 0.1, 1.6)]
+    r = ev.sv_error_rates(sv, tgt, imp)
+    assert r["threshold"] == sv.threshold and r["frr"] == 25.0 and r["far"] == 25.0
+    r2 = ev.sv_error_rates(sv, tgt, imp, threshold=10.0)
+    assert r2 == {"threshold": 10.0, "frr": 100.0, "far": 0.0}
+
+    class StubOsi:
+        threshold = 0.0
+
+        def score(self, audios, **kw):
+            return np.stack([a[:2] for a in audios])
+
+    osi = StubOsi()
+    enrolled = [np.array([2.0, 0.0]), np.array([0.1, 3.0]), np.array([1.0, 1.2]), np.array([-1.0, -2.0])]
+    illegal = [np.array([-3.0, -2.5]), np.array([0.5, 2.5])]
+    r = ev.osi_error_rates(osi, enrolled, [0, 1, 0, 1], illegal, threshold=0.0)
+    assert r == {"threshold": 0.0, "frr": 25.0, "ier": 25.0, "far": 50.0}
+
+
+def test_enrolment_directory_conventions(tmp_path):
+    """utt_id = file name up to the first '.', spk_id = utt_id up to the first '-' (build_spk_models.py:81-83); 16 kHz 16-bit wav only."""
+    from scipy.io import wavfile
+    from fakebob_b200 import build_spk_models as bsm
+    d = tmp_path / "enrollment-set"
+    d.mkdir()
+    for name, fs in (("1580-141083-0000.wav", 16000), ("61-70968-0001.wav", 16000)):
+        wavfile.write(str(d / name), fs, (np.arange(1600) % 100).astype(np.int16))
+    utt, spk, paths = bsm.list_audio_dir(str(d))
+    assert utt == ["1580-141083-0000", "61-70968-0001"] and spk == ["1580", "61"]
+    a = bsm.read_wav_int16(paths[0])
+    assert a.dtype == np.int16 and a.shape == (1600,)
+    wavfile.write(str(d / "bad-1.wav"), 8000, np.zeros(800, np.int16))
+    with pytest.raises(ValueError):
+        bsm.read_wav_int16(str(d / "bad-1.wav"))
+    wavfile.write(str(d / "bad-2.wav"), 16000, np.zeros(800, np.float32))
+    with pytest.raises(ValueError):
+        bsm.read_wav_int16(str(d / "bad-2.wav"))
+
+
+def test_utterance_sharding_covers_every_utterance_once():
+    from fakebob_b200.sharding import attack_many, utterance_range
+
+    for n, world in ((32, 8), (5, 2), (3, 8), (0, 4)):
+        got = []
+        for r in range(world):
+            lo, hi = utterance_range(n, r, world)
+            assert 0 <= lo <= hi <= n
+            got += list(range(lo, hi))
+        assert got == list(range(n))
+
+    class StubAttacker:
+        seed, draws = 7, 0
+
+        def attack(self, audio, checkpoint_path, **kw):
+            return (self.seed, self.draws, float(audio.sum()), kw), 1
+
+    audios = [np.full(4, i, dtype=np.float64) for i in range(5)]
+    a = attack_many(StubAttacker, audios, rank=1, world=2, threshold=lambda u: 10.0 + u, target=2)
+    assert sorted(a) == [2, 3, 4]
+    whole = attack_many(StubAttacker, audios, threshold=lambda u: 10.0 + u, target=2)
+    for u in a:
+        assert a[u] == whole[u]                                   # same per-utterance seed whatever the sharding
+        assert a[u][0][3] == {"threshold": 10.0 + u, "target": 2}
+    assert len({whole[u][0][0] for u in whole}) == 5              # distinct streams per utterance
