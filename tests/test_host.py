@@ -4,6 +4,7 @@ import ctypes
 import os
 import pickle
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -305,3 +306,57 @@ def test_utterance_sharding_covers_every_utterance_once():
         assert a[u] == whole[u]                                   # same per-utterance seed whatever the sharding
         assert a[u][0][3] == {"threshold": 10.0 + u, "target": 2}
     assert len({whole[u][0][0] for u in whole}) == 5              # distinct streams per utterance
+
+
+def test_dropin_modules_resolve_reference_imports():
+    """With fakebob_b200/dropin first on sys.path, the import lines of the reference's attackMain.py (:15-21) and test.py
+    (:8-13) resolve to this package's classes, whose constructors and methods take the reference's arguments."""
+    import inspect
+    import subprocess
+    code = (
+        "from FAKEBOB import FakeBob\n"
+        "from gmm_ubm_CSI import gmm_CSI\nfrom gmm_ubm_OSI import gmm_OSI\nfrom gmm_ubm_SV import gmm_SV\n"
+        "from ivector_PLDA_CSI import iv_CSI\nfrom ivector_PLDA_OSI import iv_OSI\nfrom ivector_PLDA_SV import iv_SV\n"
+        "import fakebob_b200.FAKEBOB as F, fakebob_b200.gmm_scorers as G, fakebob_b200.iv_scorers as I\n"
+        "assert FakeBob is F.FakeBob and gmm_CSI is G.gmm_CSI and gmm_OSI is G.gmm_OSI and gmm_SV is G.gmm_SV\n"
+        "assert iv_CSI is I.iv_CSI and iv_OSI is I.iv_OSI and iv_SV is I.iv_SV\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "fakebob_b200", "dropin"), ROOT]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+    from fakebob_b200.FAKEBOB import FakeBob
+    from fakebob_b200.gmm_scorers import gmm_CSI, gmm_OSI, gmm_SV
+    from fakebob_b200.iv_scorers import iv_CSI, iv_OSI, iv_SV
+
+    def names(fn):
+        return [p for p in inspect.signature(fn).parameters if p != "self"]
+    # reference signatures (SURVEY.md section 8b); keyword-only extras may follow
+    assert names(FakeBob.__init__)[:13] == ["task", "attack_type", "model", "adver_thresh", "epsilon", "max_iter", "max_lr", "min_lr",
+                                            "samples_per_draw", "sigma", "momentum", "plateau_length", "plateau_drop"]
+    assert names(FakeBob.attack) == ["audio", "checkpoint_path", "threshold", "true", "target", "fs", "bits_per_sample", "n_jobs", "debug"]
+    assert names(FakeBob.estimate_threshold) == ["audio", "fs", "bits_per_sample", "n_jobs", "debug"]
+    assert names(gmm_CSI.__init__)[:3] == ["group_id", "model_list", "pre_model_dir"]
+    assert names(gmm_OSI.__init__)[:5] == ["group_id", "model_list", "ubm", "pre_model_dir", "threshold"]
+    assert names(gmm_SV.__init__)[:5] == ["spk_id", "model", "ubm", "pre_model_dir", "threshold"]
+    assert names(iv_CSI.__init__)[:3] == ["group_id", "model_list", "pre_model_dir"]
+    assert names(iv_OSI.__init__)[:4] == ["group_id", "model_list", "pre_model_dir", "threshold"]
+    assert names(iv_SV.__init__)[:4] == ["spk_id", "model", "pre_model_dir", "threshold"]
+    for cls in (gmm_CSI, gmm_OSI, gmm_SV, iv_CSI, iv_OSI, iv_SV):
+        for fn in (cls.score, cls.make_decisions):           # first argument: `audios` (gmm_*) or `audio_list` (iv_*), as in the reference
+            assert names(fn)[0] in ("audios", "audio_list") and set(names(fn)[1:]) == {"fs", "bits_per_sample", "debug", "n_jobs"}
+    ref = "/root/reference"
+    if os.path.isdir(ref):                                   # live check against the reference's own definitions
+        import ast
+        want = {}
+        for mod in ("FAKEBOB", "gmm_ubm_CSI", "gmm_ubm_OSI", "gmm_ubm_SV", "ivector_PLDA_CSI", "ivector_PLDA_OSI", "ivector_PLDA_SV"):
+            tree = ast.parse(open(os.path.join(ref, mod + ".py")).read())
+            for node in ast.walk(tree):
+                if isinstance(node, ast.ClassDef):
+                    for fn in node.body:
+                        if isinstance(fn, ast.FunctionDef) and fn.name in ("__init__", "score", "make_decisions", "attack", "estimate_threshold"):
+                            want[(node.name, fn.name)] = [a.arg for a in fn.args.args if a.arg != "self"]
+        ours = {"FakeBob": FakeBob, "gmm_CSI": gmm_CSI, "gmm_OSI": gmm_OSI, "gmm_SV": gmm_SV, "iv_CSI": iv_CSI, "iv_OSI": iv_OSI, "iv_SV": iv_SV}
+        assert len(want) >= 20
+        for (cname, fname), args in want.items():
+            got = names(getattr(ours[cname], fname))
+            assert got[:len(args)] == args, (cname, fname, args, got)
