@@ -621,10 +621,11 @@ extern "C" int fb_nes_run(fb_ctx *ctx, int n_iters, const double *noise_host) {
 extern "C" int fb_nes_status(fb_ctx *ctx, int *iters_done, int *stopped) {
   FB_CHECK_ARG(ctx && ctx->nes, "fb_nes_init has not been called");
   int h[4];
+  int err[2] = {0, 0};
+  // both read-backs ride the stream, one host wait for the pair
   FB_CUDA(cudaMemcpyAsync(h, ctx->nes->flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(cudaMemcpyAsync(err, ctx->misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FB_CUDA(cudaStreamSynchronize(ctx->stream));
-  int err[2];
-  FB_CUDA(cudaMemcpy(err, ctx->misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost));
   if (err[0] != 0) {
     fb_set_error("NES batch failed on device (code %d: >=16 utterance without voiced frames, 2 utterance too long, 3 matrix not SPD)", err[0]);
     return FB_ERR_NO_VOICED;
