@@ -154,3 +154,29 @@ def test_shared_variance_chain_matches_general_kernel(small_tree, monkeypatch):
     assert np.abs((a[:, 1:] - a[:, :1]) - (b[:, 1:] - b[:, :1])).max() < 5e-5
     shared.close()
     general.close()
+
+
+def test_cuda_path_matches_committed_stage_fixture():
+    """The CUDA front-end and GMM kernel against tests/golden/kaldi_stages.npz (a committed artefact of the oracle, see
+    tests/golden/make_golden_kaldi.py) -- independent of the oracle's current code."""
+    import os
+    from fakebob_b200.engine import GmmEngine
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kaldi_stages.npz"))
+    models = [{"weights": g["ubm_weights"], "means_invvars": g["ubm_means_invvars"], "inv_vars": g["ubm_inv_vars"], "gconsts": g["ubm_gconsts"]},
+              {"weights": g["ubm_weights"], "means_invvars": g["spk_means_invvars"], "inv_vars": g["ubm_inv_vars"], "gconsts": g["spk_gconsts"]}]
+    eng = GmmEngine(models)
+    eng.set_debug(True)
+    avg = eng.score_avg_ll([np.ascontiguousarray(g["wave"])])
+    st = eng.last_stages()
+    assert st["mfcc"].shape == g["mfcc"].shape and np.abs(st["mfcc"] - g["mfcc"]).max() < TOL_MFCC
+    assert np.array_equal(st["vad"] >= 0, g["vad"] != 0)
+    assert np.abs(st["feats"] - g["voiced_feats"]).max() < TOL_FEAT
+    assert np.abs(st["frame_ll"][0] - g["frame_ll_ubm"]).max() < TOL_FRAME_LL
+    assert np.abs(st["frame_ll"][1] - g["frame_ll_spk"]).max() < TOL_FRAME_LL
+    assert np.abs(avg[0] - g["avg_ll"]).max() < TOL_AVG_LL
+    # enrolment against the fixture's MAP-adapted model
+    one = GmmEngine(models[:1])
+    half = one.map_adapt([np.ascontiguousarray(g["wave"])], mean_tau=10.0)       # all voiced frames (the fixture used every 2nd)
+    assert half["means_invvars"].shape == g["spk_means_invvars"].shape and np.isfinite(half["gconsts"]).all()
+    one.close()
+    eng.close()

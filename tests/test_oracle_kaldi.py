@@ -98,3 +98,26 @@ def test_map_adaptation_moves_means_toward_data():
 def test_int16_truncation_toward_zero():
     a = np.array([0.99999, -0.99999, 1.4 / 32768, -1.6 / 32768])
     assert kf.float_to_int16(a).tolist() == [32767, -32767, 1, -1]
+
+
+def test_oracle_reproduces_committed_stage_fixture():
+    """tests/golden/kaldi_stages.npz (made by tests/golden/make_golden_kaldi.py) freezes the oracle's per-stage arithmetic."""
+    import os
+    from oracle import kaldi_feats as kf
+    from oracle.diag_gmm import DiagGmm
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kaldi_stages.npz"))
+    wave = g["wave"]
+    m = kf.mfcc(wave)
+    v = kf.compute_vad(m)
+    f = kf.sliding_cmn(kf.add_deltas(m))[v != 0]
+    assert m.shape == g["mfcc"].shape and np.abs(m - g["mfcc"]).max() < 2e-4        # BLAS / libm builds may differ in the last bits
+    assert np.array_equal(v != 0, g["vad"] != 0) and 0 < int((v != 0).sum()) < m.shape[0]
+    assert np.abs(f - g["voiced_feats"]).max() < 2e-4
+    ubm = DiagGmm(g["ubm_weights"], g["ubm_means_invvars"], g["ubm_inv_vars"], g["ubm_gconsts"])
+    spk = DiagGmm(g["ubm_weights"], g["spk_means_invvars"], g["ubm_inv_vars"], g["spk_gconsts"])
+    X = g["voiced_feats"]
+    assert np.abs(ubm.frame_loglikes(X) - g["frame_ll_ubm"]).max() < 2e-4
+    assert np.abs(spk.frame_loglikes(X) - g["frame_ll_spk"]).max() < 2e-4
+    assert abs(float(ubm.avg_loglike(X)) - g["avg_ll"][0]) < 1e-4 and abs(float(spk.avg_loglike(X)) - g["avg_ll"][1]) < 1e-4
+    re = ubm.map_adapt_means(X[::2], tau=10.0)
+    assert np.abs(re.means_invvars - g["spk_means_invvars"]).max() < 2e-4 and np.abs(re.gconsts - g["spk_gconsts"]).max() < 2e-4
