@@ -360,3 +360,20 @@ def test_dropin_modules_resolve_reference_imports():
         for (cname, fname), args in want.items():
             got = names(getattr(ours[cname], fname))
             assert got[:len(args)] == args, (cname, fname, args, got)
+
+
+def test_library_contains_sm100a_tensor_core_and_tma_code():
+    """The built library carries sm_100a SASS with tcgen05 MMAs (UTCHMMA), TMEM loads (LDTM), smem->TMEM copies (UTCCP) and
+    TMA bulk copies (UBLKCP) -- i.e. the GMM hot path is the hand-written Blackwell kernel, not a generic fallback."""
+    import shutil
+    import subprocess
+    from fakebob_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    elf = subprocess.run([cuobjdump, "--list-elf", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    assert "sm_100a" in elf, elf[:400]
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_Z15gmm_umma_kernelILb0ELb1EEv7GmmArgs", _lib.LIB_PATH],
+                          capture_output=True, text=True, timeout=300).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTCCP", "UBLKCP", "SYNCS.PHASECHK"):
+        assert mnemonic in sass, mnemonic
