@@ -50,7 +50,12 @@ class FakeBob(object):
         self.rng = rng or os.environ.get("FAKEBOB_RNG", "philox")
         if self.rng not in ("philox", "numpy"):
             raise ValueError("rng must be 'philox' or 'numpy'")
-        self.seed = int(np.random.randint(0, 2 ** 62)) if seed is None else int(seed)
+        # the Philox key comes from numpy's global generator (so np.random.seed still makes runs reproducible); in 'numpy'
+        # mode nothing is drawn here, so the per-iteration np.random.normal stream is exactly the reference's
+        if seed is not None:
+            self.seed = int(seed)
+        else:
+            self.seed = int(np.random.randint(0, 2 ** 62)) if self.rng == "philox" else 0
         self.verbose = (os.environ.get("FAKEBOB_VERBOSE", "1") != "0") if verbose is None else verbose
         self.iters_per_launch = max(1, int(iters_per_launch))
         self.draws = 0                 # Philox draw counter == number of get_grad evaluations so far

@@ -45,7 +45,8 @@ _SIGS = {
     "fb_set_feature_config": (C.c_int, [_P, C.POINTER(FeatConfig)]),
     "fb_load_diag_gmm": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "fb_finalize_gmms": (C.c_int, [_P, C.c_int]),
-    "fb_set_gmm_impl": (C.c_int, [_P, C.c_int]),
+    "fb_set_gmm_delta_terms": (C.c_int, [_P, C.c_int]),
+    "fb_get_gmm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "fb_score_gmm_host": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "fb_score_gmm_dev": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "fb_map_adapt_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, _P, _P, _P]),
@@ -55,6 +56,7 @@ _SIGS = {
     "fb_set_enrolled_ivectors": (C.c_int, [_P, _P, C.c_int]),
     "fb_score_ivector_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "fb_get_posteriors": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "fb_get_ivector_stats": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "fb_set_debug": (C.c_int, [_P, C.c_int]),
     "fb_get_num_frames": (C.c_int, [_P, C.c_int, _P, _P]),
     "fb_get_mfcc": (C.c_int, [_P, _P, C.c_int64]),

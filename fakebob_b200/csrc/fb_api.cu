@@ -75,7 +75,7 @@ extern "C" int fb_ctx_destroy(fb_ctx *ctx) {
   fb_nes_destroy(ctx);
   fb_ivector_destroy(ctx);
   fb_comm_destroy_impl(ctx);
-  ctx->w_img.release(); ctx->gconst2.release(); ctx->w_f32.release(); ctx->gconst_nat.release();
+  ctx->w_img.release();
   ctx->wave.release(); ctx->wave_off.release(); ctx->frame_off.release(); ctx->mfcc.release();
   ctx->vrank.release(); ctx->nvoiced.release(); ctx->row_off.release(); ctx->misc.release();
   ctx->a_img.release(); ctx->raw72.release(); ctx->cmn_prefix.release(); ctx->feats_f32.release(); ctx->part.release();
@@ -111,10 +111,17 @@ extern "C" int fb_set_feature_config(fb_ctx *ctx, const fb_feat_config *cfg) {
   return FB_OK;
 }
 
-extern "C" int fb_set_gmm_impl(fb_ctx *ctx, int impl) {
-  FB_CHECK_ARG(ctx && (impl == 0 || impl == 1), "impl must be 0 (tcgen05) or 1 (fp32 cross-check)");
-  ctx->gmm_impl = impl;
-  fb_bump_alloc_epoch();
+extern "C" int fb_set_gmm_delta_terms(fb_ctx *ctx, int terms) {
+  FB_CHECK_ARG(ctx && terms >= 0 && terms <= 3, "terms must be 0 (automatic), 1, 2 or 3");
+  ctx->delta_terms_req = terms;
+  return FB_OK;
+}
+
+extern "C" int fb_get_gmm_info(fb_ctx *ctx, int *shared_variances, int *delta_terms, double *err_estimate) {
+  FB_CHECK_ARG(ctx && ctx->n_models > 0, "no GMMs loaded (fb_finalize_gmms)");
+  if (shared_variances) *shared_variances = ctx->gmm_shared ? 1 : 0;
+  if (delta_terms) *delta_terms = ctx->gmm_shared ? ctx->delta_terms : 3;
+  if (err_estimate) *err_estimate = ctx->gmm_shared ? ctx->delta_err_est : 0.0;
   return FB_OK;
 }
 
@@ -126,18 +133,33 @@ extern "C" int fb_set_debug(fb_ctx *ctx, int keep_f32_features) {
   return FB_OK;
 }
 
-static int check_voiced(fb_ctx *ctx) {
-  int misc[3];
-  FB_CUDA(cudaMemcpyAsync(misc, ctx->misc.p, sizeof(misc), cudaMemcpyDeviceToHost, ctx->stream));
+// Device-side failure flag misc[1] (set by the kernels, 0 = none): 2 = utterance too long for a kernel's per-utterance
+// capacity, 3 = matrix not positive definite, 16 + b = utterance b has no voiced frames.  Reads it on the context's stream
+// (so it also waits for the enqueued work), clears it, and maps it to a distinct error code.
+int fb_check_device_error(fb_ctx *ctx) {
+  int code = 0;
+  FB_CUDA(cudaMemcpyAsync(&code, ctx->misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (misc[1] != 0) {
-    const int zero = 0;
-    cudaMemcpy(ctx->misc.p + 1, &zero, sizeof(int), cudaMemcpyHostToDevice);
-    fb_set_error("utterance %d has no voiced frames (Kaldi's select-voiced-frames would drop it)", misc[1] - 16);
-    return FB_ERR_NO_VOICED;
-  }
-  return FB_OK;
+  return fb_map_device_error(ctx, code);
 }
+
+int fb_map_device_error(fb_ctx *ctx, int code) {
+  if (code == 0) return FB_OK;
+  FB_CUDA(cudaMemsetAsync(ctx->misc.p + 1, 0, sizeof(int), ctx->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (code == 2) {
+    fb_set_error("an utterance is too long for the i-vector statistics kernel");
+    return FB_ERR_TOO_LONG;
+  }
+  if (code == 3) {
+    fb_set_error("i-vector posterior precision matrix (quad + I) is not positive definite");
+    return FB_ERR_NOT_SPD;
+  }
+  fb_set_error("utterance %d has no voiced frames (Kaldi's select-voiced-frames would drop it)", code - 16);
+  return FB_ERR_NO_VOICED;
+}
+
+static int check_voiced(fb_ctx *ctx) { return fb_check_device_error(ctx); }
 
 static int score_common(fb_ctx *ctx, const int64_t *offsets, int B) {
   int rc;

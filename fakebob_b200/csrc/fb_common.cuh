@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -111,12 +112,11 @@ struct fb_ctx {
   // models
   FbHostGmm host_gmm[FB_MAX_MODELS];
   int n_models = 0, C = 0;
-  int gmm_impl = 0;
-  DevBuf<__half> w_img;        // general: [model][C/64][hi 20 | lo 20 slabs][64][8]; shared-variance: [C/64][1+models][hi 10 | lo 10][64][8]
+  int delta_terms_req = 0;     // fb_set_gmm_delta_terms: 0 = automatic
+  int delta_terms = 3;         // fp16 product terms of the (slot m - slot 0) sub-stages actually in use (shared-variance mode)
+  DevBuf<__half> w_img;        // general: [model][C/64][hi 20 | lo 20 slabs][64][8]; shared-variance: [C/64][x^2 | slot 0 | slot m - slot 0 ...]
   bool gmm_shared = false;     // all models share inv_vars (MAP mean-only adaptation): x^2 contraction done once
-  DevBuf<float>  gconst2;      // [model][C]  gconst * log2(e)
-  DevBuf<float>  w_f32;        // [model][C][144] (means_invvars | -0.5 inv_vars), cross-check kernel
-  DevBuf<float>  gconst_nat;   // [model][C]
+  double delta_err_est = 0.0;  // predicted per-frame error of a one-term difference product (fb_finalize_gmms)
 
   // batch workspace (shared by score() calls [tag 0] and the NES state [tag 1])
   int batch_tag = -1;
@@ -165,12 +165,12 @@ int fb_run_frontend(fb_ctx *ctx);             // mfcc -> vad_scan -> feats (wave
 // fb_gmm.cu
 int fb_run_gmm(fb_ctx *ctx);                  // gmm -> reduce into avg_ll
 void fb_prof_mark(fb_ctx *ctx, int tag);
+int fb_check_device_error(fb_ctx *ctx);       // reads + clears misc[1] on the stream; distinct error codes
+int fb_map_device_error(fb_ctx *ctx, int code);
 // helpers
 // cudaFuncSetAttribute is per device: one flag per device ordinal (a process may hold contexts on several GPUs)
-static inline bool fb_once_per_device(unsigned long long &mask, int device) {
+static inline bool fb_once_per_device(std::atomic<unsigned long long> &mask, int device) {
   const unsigned long long bit = 1ull << (device & 63);
-  if (mask & bit) return false;
-  mask |= bit;
-  return true;
+  return (mask.fetch_or(bit) & bit) == 0;
 }
 static inline int fb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -97,12 +97,7 @@ extern "C" int fb_map_adapt_host(fb_ctx *ctx, const int16_t *wave, const int64_t
     fb_set_error("enrolment read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
     return done(FB_ERR_CUDA);
   }
-  if (misc[1] != 0) {
-    const int zero = 0;
-    cudaMemcpy(ctx->misc.p + 1, &zero, sizeof(int), cudaMemcpyHostToDevice);
-    fb_set_error("utterance %d has no voiced frames (Kaldi's select-voiced-frames would drop it)", misc[1] - 16);
-    return done(FB_ERR_NO_VOICED);
-  }
+  if (misc[1] != 0) return done(fb_map_device_error(ctx, misc[1]));
   // MapDiagGmmUpdate (means only) + CopyToDiagGmm + ComputeGconsts, double arithmetic, float storage
   const FbHostGmm &g = ctx->host_gmm[0];
   const double *occ = h.data(), *macc = h.data() + C;

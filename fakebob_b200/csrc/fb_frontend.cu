@@ -622,7 +622,7 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   fb_prof_mark(ctx, 2);
   const size_t smem = fb_feats_smem_bytes(ctx->max_frames);
   const int use_smem = smem <= FB_FEATS_SMEM_MAX;
-  static unsigned long long configured_mask = 0;
+  static std::atomic<unsigned long long> configured_mask{0};
   if (fb_once_per_device(configured_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(feats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_FEATS_SMEM_MAX));
   }

@@ -35,10 +35,17 @@
 // Work = the sequence of 64-column stages ordered (super-tile, [model,] stage), cut into 148 equal contiguous ranges; a CTA
 // writes one (max, sum) partial per row and segment (run of its stages inside one super-tile), gmm_frame_kernel recomputes
 // the cut points to merge them.
+// Shared-variance mode (all slots share their inverse variances, as MAP mean-only adaptation produces): per (rows, 64-column
+// stage) the ring carries  q = 0: x^2 . (-0.5/var),  q = 1: x . w_0 + g_0  (slot 0, normally the UBM),
+// q = 1 + m: x . (w_m - w_0) + (g_m - g_0)  for every other slot, and the epilogue forms  ll_0 = Q + T_0,  ll_m = ll_0 + D_m.
+// Q and T_0 always use the three-term split; the difference sub-stages use `delta_terms` of the three products
+// (1: hi.hi, 2: hi.hi + hi.lo, 3: all) -- the differences are small, so their fp16 rounding error is small in absolute
+// terms (scripts/gmm_precision_study.py; fb_set_gmm_delta_terms in the header).
 // Tried and rejected (same-clock A/B, cycles per CTA): 16 epilogue warps of 32 columns (+5 %); four accumulators (two per
 // tile, no cross-tile coupling) with the x^2-lo operand kept in shared memory and a 4-slot ring (+7 %).
 #include "fb_common.cuh"
 #include <math.h>
+#include <atomic>
 
 #ifndef GMM_PARTS
 #define GMM_PARTS 3
@@ -183,7 +190,26 @@ struct GmmArgs {
   const int *done_flag;
   float *ll_out;            // STORE mode: [rows_cap][C] natural-log component log-likelihoods (Gaussian selection)
   int n_models, C, rows_cap;
+  int delta_terms;          // shared mode: fp16 product terms of the difference sub-stages (1, 2 or 3)
 };
+
+// Shared-mode ring entries of one 64-column stage: entry 0 = {q = 0, q = 1} (2 x 20 KB: hi + lo), then the difference
+// sub-stages in groups that fill a 40 KB slot: 4 per entry when only their hi half is stored (delta_terms == 1, 10 KB each),
+// else 2 per entry.
+struct SharedLayout {
+  uint32_t dbytes;          // bytes of one difference sub-stage in the W image
+  uint32_t group;           // difference sub-stages per ring entry
+  uint32_t stage_bytes;     // bytes of one stage of the W image
+  uint32_t mask;            // product terms of a difference sub-stage: bit 0 hi.hi, bit 1 lo.hi, bit 2 hi.lo
+};
+__host__ __device__ __forceinline__ SharedLayout shared_layout(int n_models, int delta_terms) {
+  SharedLayout L;
+  L.dbytes = (delta_terms == 1) ? 10240u : 20480u;
+  L.group = 40960u / L.dbytes;
+  L.stage_bytes = 40960u + (uint32_t)(n_models - 1) * L.dbytes;
+  L.mask = (delta_terms == 1) ? 1u : (delta_terms == 2 ? 5u : 7u);
+  return L;
+}
 
 // 64 accumulator columns of one row: online max / sum of 2^(v - max) with Kaldi's cutoff (LogSumExp drops terms below
 // max + log(FLT_EPSILON) = max - 23 in log2).  Only ~0.5 % of the terms survive that cutoff, so the exponentials are
@@ -272,7 +298,8 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   const long long n_units = (long long)n_super * models_per_unit * nst;
   const int u0 = (int)(n_units * blockIdx.x / gridDim.x);
   const int u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
-  const int n_sub = kShared ? g.n_models + 1 : 1;                              // ring entries per 64-column stage
+  const int n_sub = kShared ? g.n_models + 1 : 1;                              // sub-stages (jobs per tile) per 64-column stage
+  const SharedLayout SL = shared_layout(g.n_models, g.delta_terms);
 
   if (warp == 0 && lane == 0) {
     for (uint32_t i = 0; i < kNumSlots; ++i) {
@@ -326,23 +353,40 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         }
         cur_super = sp;
       }
-      {
-        // a bulk copy costs ~930 clk whatever its size (<= 40 KB) and copies of one SM do not overlap, so the shared
-        // mode fetches its 20 KB sub-stages two per ring entry
+      if constexpr (kShared) {
+        // a bulk copy costs ~930 clk whatever its size (<= 40 KB) and copies of one SM do not overlap, so the sub-stages
+        // are fetched in groups that fill a slot: {x^2, slot 0}, then `group` difference sub-stages per entry
+        const uint8_t *wst = reinterpret_cast<const uint8_t *>(g.w_img) + stage * (size_t)SL.stage_bytes;
+        const int n_delta = g.n_models - 1;
 #pragma unroll 1
-        for (int q = 0; q < n_sub; q += kShared ? 2 : 1) {
+        for (int e = -1; e * (int)SL.group < n_delta; ++e) {
           const uint32_t slot = cnt % kNumSlots;
           STAT_WAIT(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
           if (elect_one()) {
-            const uint32_t bytes = kShared ? ((q + 1 < n_sub) ? 2 * kWShBytes : kWShBytes) : kWStageBytes;
-            const size_t off = kShared ? (stage * n_sub + q) * (size_t)kWShBytes
-                                       : ((size_t)model * (g.C / FB_STAGE_N) + stage) * (size_t)kWStageBytes;
+            uint32_t bytes, off;
+            if (e < 0) { bytes = 40960u; off = 0; }
+            else {
+              const int first = e * (int)SL.group;
+              const int n = min((int)SL.group, n_delta - first);
+              bytes = (uint32_t)n * SL.dbytes;
+              off = 40960u + (uint32_t)first * SL.dbytes;
+            }
             mbar_expect_tx(bar_full + 8 * slot, bytes);
-            bulk_g2s(base + slot * kSlotBytes, reinterpret_cast<const uint8_t *>(g.w_img) + off, bytes, bar_full + 8 * slot);
+            bulk_g2s(base + slot * kSlotBytes, wst + off, bytes, bar_full + 8 * slot);
           }
           __syncwarp();
           ++cnt;
         }
+      } else {
+        const uint32_t slot = cnt % kNumSlots;
+        STAT_WAIT(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+        if (elect_one()) {
+          const size_t off = ((size_t)model * (g.C / FB_STAGE_N) + stage) * (size_t)kWStageBytes;
+          mbar_expect_tx(bar_full + 8 * slot, kWStageBytes);
+          bulk_g2s(base + slot * kSlotBytes, reinterpret_cast<const uint8_t *>(g.w_img) + off, kWStageBytes, bar_full + 8 * slot);
+        }
+        __syncwarp();
+        ++cnt;
       }
     }
 #ifdef GMM_STATS
@@ -395,13 +439,22 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
         for (int q = 0; q < n_sub; ++q) {
           const uint32_t slot = cnt % kNumSlots;
-          const bool first_in_slot = !kShared || (q & 1) == 0;
-          const bool last_in_slot = !kShared || (q & 1) == 1 || q + 1 == n_sub;
+          // position of sub-stage q inside its ring entry (shared mode: {0, 1}, then groups of difference sub-stages)
+          bool first_in_slot = true, last_in_slot = true;
+          uint32_t sub_off = 0, half_bytes = kWHalfBytes, mask = 7u;
+          if constexpr (kShared) {
+            if (q < 2) {
+              first_in_slot = q == 0; last_in_slot = q == 1; sub_off = q ? kWShBytes : 0; half_bytes = kWShHalfBytes;
+            } else {
+              const uint32_t j = (uint32_t)(q - 2), r = j % SL.group;
+              first_in_slot = r == 0; last_in_slot = r == SL.group - 1 || q + 1 == n_sub;
+              sub_off = r * SL.dbytes; half_bytes = kWShHalfBytes; mask = SL.mask;
+            }
+          }
           if (first_in_slot) STAT_WAIT(st_mma_full, bar_full + 8 * slot, (cnt / kNumSlots) & 1);
-          const uint32_t sub_off = (kShared && (q & 1)) ? kWShBytes : 0;
           const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes + sub_off) & 0x3FFFFu) >> 4);
-          const uint64_t w_lo = w_hi + (uint64_t)((kShared ? kWShHalfBytes : kWHalfBytes) >> 4);
-          // shared mode: q = 0 is the x^2 sub-step, q >= 1 the x (+ gconst) sub-step of model q-1; all start from zero
+          const uint64_t w_lo = w_hi + (uint64_t)(half_bytes >> 4);
+          // shared mode: q = 0 is the x^2 sub-step, q >= 1 the x (+ gconst) sub-steps; all start from zero
           const uint32_t a_off = (kShared && q == 0) ? kTmemX2Cols : 0;
           const uint32_t abuf = job % kNumAcc;
           // accumulator abuf was last used by job - 3, a job of the other tile: wait until that tile's epilogue has read it
@@ -414,6 +467,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
             constexpr int nkb = kShared ? 5 : 10;
 #pragma unroll
             for (int part = 0; part < GMM_PARTS; ++part) {
+              if (!((mask >> part) & 1u)) continue;
               const uint32_t a_base = (part == 1) ? a_lo : a_hi;
               const uint64_t b_base = (part == 2) ? w_lo : w_hi;
 #pragma unroll
@@ -491,7 +545,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       }
       {
         if constexpr (kShared) {
-          float qa[32], qb[32];                         // the x^2 term Q of this (rows, 64-column stage)
+          float qa[32], qb[32];                         // Q (x^2 term), then ll_0 = Q + T_0: the base every other slot adds to
           fetch(qa, qb);
 #pragma unroll 1
           for (int r = 0; r < g.n_models; ++r) {
@@ -502,6 +556,10 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
               const float2 t0 = __fadd2_rn(make_float2(va[i], va[i + 1]), make_float2(qa[i], qa[i + 1]));
               const float2 t1 = __fadd2_rn(make_float2(vb[i], vb[i + 1]), make_float2(qb[i], qb[i + 1]));
               va[i] = t0.x; va[i + 1] = t0.y; vb[i] = t1.x; vb[i + 1] = t1.y;
+            }
+            if (r == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { qa[i] = va[i]; qb[i] = vb[i]; }
             }
             float m = mm[r], sacc = ss[r];
 #ifndef GMM_NO_LSE
@@ -557,57 +615,6 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fp32 CUDA-core cross-check kernel (debug / bring-up): same partial format, operands rebuilt
-// from the hi+lo image so it sees exactly the features the tensor-core kernel sees.
-// grid (rows/32, n_models * nch), block 128: each thread = one column of the 128-column chunk.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-gmm_simt_kernel(const __half *__restrict__ a_img, const float *__restrict__ w_f32, const float *__restrict__ gconst_nat,
-                const float *__restrict__ feat_scale, float2 *__restrict__ part, const int *__restrict__ misc,
-                int n_models, int C, int rows_cap) {
-  __shared__ float s_x[32][2 * FB_DIM + 1];
-  __shared__ float s_ll[32][FB_CHUNK_N + 1];
-  const int M = misc[2];
-  const int row0 = blockIdx.x * 32;
-  if (row0 >= M) return;
-  const int nch = C / FB_CHUNK_N;
-  const int model = blockIdx.y / nch, ch = blockIdx.y % nch;
-  for (int idx = threadIdx.x; idx < 32 * 2 * FB_DIM; idx += blockDim.x) {
-    const int r = idx / (2 * FB_DIM), k = idx % (2 * FB_DIM);
-    const int row = row0 + r;
-    const int tile = row >> 7, rr = row & 127, e = k & 7;
-    const int slab = (k < FB_DIM) ? (k >> 3) : (FB_SLAB_X2 + ((k - FB_DIM) >> 3));
-    const size_t b = ((size_t)tile * FB_A_TILE_SLABS + slab) * (FB_TILE_M * 8) + rr * 8 + e;
-    float v = __half2float(a_img[b]) + __half2float(a_img[b + (size_t)FB_A_HI_SLABS * FB_TILE_M * 8]);
-    const int d = (k < FB_DIM) ? k : k - FB_DIM;
-    const float sc = feat_scale[d];
-    v = (k < FB_DIM) ? v / sc : v / (sc * sc);
-    s_x[r][k] = v;
-  }
-  __syncthreads();
-  const int c = ch * FB_CHUNK_N + threadIdx.x;
-  const float *w = w_f32 + ((size_t)model * C + c) * (2 * FB_DIM);
-  const float gcv = gconst_nat[(size_t)model * C + c];
-  for (int r = 0; r < 32; ++r) {
-    float acc = gcv;
-    for (int k = 0; k < 2 * FB_DIM; ++k) acc += w[k] * s_x[r][k];
-    s_ll[r][threadIdx.x] = acc * 1.4426950408889634f;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int r = threadIdx.x;
-    float m = -INFINITY;
-    for (int k = 0; k < FB_CHUNK_N; ++k) m = fmaxf(m, s_ll[r][k]);
-    float s = 0.f;
-    for (int k = 0; k < FB_CHUNK_N; ++k) {
-      const float t = s_ll[r][k] - m;
-      if (t >= -23.0f) s += exp2f(t);
-    }
-    part[((size_t)model * (2 * nch) + 2 * ch) * rows_cap + row0 + r] = make_float2(m, s);   // stage index of the chunk's first stage
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Merge the per-chunk partials into per-frame log-likelihoods (one thread per (row, model)), then the per-utterance
 // average (gmm-global-get-frame-likes --average=true: float frame values, double sum, float quotient).
 // Fixed reduction order (deterministic).
@@ -621,11 +628,10 @@ gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, 
   const int M = misc[2];
   if (row >= M) return;
   // The partials of this row are the segments gmm_umma_kernel cut its stage sequence into: recompute the CTA boundaries
-  // floor(total * b / grid) that fall inside this (super-tile[, model]) item.  umma_grid == 0: the fp32 cross-check kernel,
-  // one partial per 128-column chunk.
+  // floor(total * b / grid) that fall inside this (super-tile[, model]) item.
   float2 p[64];                                  // C <= 4096: at most 64 stages, hence at most 64 segments
   int n = 0;
-  if (umma_grid > 0) {
+  {
     const int n_super = (M + 2 * FB_TILE_M - 1) / (2 * FB_TILE_M);
     const long long total = (long long)n_super * models_per_unit * nst;
     const int sp = row / (2 * FB_TILE_M);
@@ -638,8 +644,6 @@ gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, 
       p[n++] = part[((size_t)model * nst + (int)(st - g0)) * rows_cap + row];
       st = end;
     }
-  } else {
-    for (int k = 0; k < nst; k += 2) p[n++] = part[((size_t)model * nst + k) * rows_cap + row];
   }
   float mx = -INFINITY;
   for (int k = 0; k < n; ++k) mx = fmaxf(mx, p[k].x);
@@ -738,18 +742,6 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
   ctx->gmm_shared = shared;
   const int n_stage = C / FB_STAGE_N;
   const double log2e = 1.4426950408889634;
-  std::vector<float> gc2((size_t)n_models * C), gcn((size_t)n_models * C), wf((size_t)n_models * C * 2 * FB_DIM);
-  for (int m = 0; m < n_models; ++m) {
-    const FbHostGmm &h = ctx->host_gmm[m];
-    for (int c = 0; c < C; ++c) {
-      gc2[(size_t)m * C + c] = (float)((double)h.gconsts[c] * log2e);
-      gcn[(size_t)m * C + c] = h.gconsts[c];
-      for (int k = 0; k < 2 * FB_DIM; ++k) {
-        const int d = (k < FB_DIM) ? k : k - FB_DIM;
-        wf[((size_t)m * C + c) * 2 * FB_DIM + k] = (k < FB_DIM) ? h.means_invvars[(size_t)c * FB_DIM + d] : -0.5f * h.inv_vars[(size_t)c * FB_DIM + d];
-      }
-    }
-  }
   // scaled weights in double: w1[m][c][d] = miv / s * log2e ; w2[c][d] = -0.5 iv / s^2 * log2e ; g[m][c] = gconst * log2e
   auto w1 = [&](int m, int c, int d) {
     return (double)ctx->host_gmm[m].means_invvars[(size_t)c * FB_DIM + d] / (double)ctx->tables_host.feat_scale[d] * log2e;
@@ -780,23 +772,58 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
         put_gconst3(img, sb + (size_t)FB_SLAB_ONES * slabW, gl(m, c));
       }
   } else {
-    // [stage][q = 0: x^2 part, q = 1+m: x part + gconst of model m][hi 10 slabs | lo 10 slabs][64 cols][8]
-    const size_t sub_halfs = (size_t)2 * 10 * slabW;
-    const int n_sub = n_models + 1;
-    img.assign((size_t)n_stage * n_sub * sub_halfs, __float2half_rn(0.f));
+    // How many of the three fp16 products the difference sub-stages need.  The rounding error of a one-term product
+    // x_hi . dw_hi is ~2^-12 |x| |dw| per dimension; with |x| ~ 1 after the power-of-two scaling, the per-frame error of
+    // component c is ~2^-12 ||dw_c||.  E = 2^-12 sqrt(sum_c weight_c ||dw_c||^2), maximised over the slots, predicts it
+    // (scripts/gmm_precision_study.py: E = 6e-4 <-> frame error 7e-4 rms, utterance score deviation 1.1e-4 with one term,
+    // 4e-5 with two).  The automatic choice keeps the predicted score deviation below the 1e-4 resolution of the
+    // reference's 7-significant-digit text scores.
+    double E = 0.0;
+    for (int m = 1; m < n_models; ++m) {
+      double acc = 0.0, wsum = 0.0;
+      for (int c = 0; c < C; ++c) {
+        double n2 = 0.0;
+        for (int d = 0; d < FB_DIM; ++d) { const double dv = w1(m, c, d) - w1(0, c, d); n2 += dv * dv; }
+        acc += (double)g0.weights[c] * n2;
+        wsum += g0.weights[c];
+      }
+      const double e = ldexp(sqrt(acc / (wsum > 0 ? wsum : 1.0)), -12);
+      if (e > E) E = e;
+    }
+    ctx->delta_err_est = E;
+    int terms = ctx->delta_terms_req;
+    if (terms == 0) terms = (E <= 8e-4) ? 1 : ((E <= 2.5e-3) ? 2 : 3);
+    ctx->delta_terms = terms;
+    // [stage][q = 0: x^2 part | q = 1: x part + gconst of slot 0 | q = 1+m: (slot m - slot 0) x part + gconst difference]
+    // q < 2: [hi 10 slabs | lo 10 slabs][64 cols][8]; q >= 2: the same, or the hi half alone when terms == 1
+    const SharedLayout SL = shared_layout(n_models, terms);
+    const size_t stage_halfs = SL.stage_bytes / 2;
+    img.assign((size_t)n_stage * stage_halfs, __float2half_rn(0.f));
     const size_t lo_off = (size_t)10 * slabW;
+    std::vector<__half> scratch(2 * lo_off + 16);
     for (int c = 0; c < C; ++c) {
       const int st = c / FB_STAGE_N, cc = c % FB_STAGE_N;
-      for (int q = 0; q < n_sub; ++q) {
-        const size_t sb = ((size_t)st * n_sub + q) * sub_halfs + (size_t)cc * 8;
+      for (int q = 0; q <= n_models; ++q) {
+        const size_t q_off = (q < 2) ? (size_t)q * 10240 : (size_t)20480 + (size_t)(q - 2) * (SL.dbytes / 2);   // in halfs
+        const size_t sb = (size_t)st * stage_halfs + q_off + (size_t)cc * 8;
+        const bool has_lo = q < 2 || terms >= 2;
         for (int d = 0; d < FB_DIM; ++d) {
           double v;
           if (q == 0) v = w2(0, c, d);
-          else v = w1(q - 1, c, d);
+          else if (q == 1) v = w1(0, c, d);
+          else v = w1(q - 1, c, d) - w1(0, c, d);
           if (!(fabs(v) < 60000.0)) range_err = true;
-          put_split(img, sb + (size_t)(d >> 3) * slabW + (d & 7), lo_off, v);
+          const size_t idx = sb + (size_t)(d >> 3) * slabW + (d & 7);
+          if (has_lo) put_split(img, idx, lo_off, v);
+          else img[idx] = __float2half_rn((float)v);
         }
-        if (q >= 1) put_gconst3(img, sb + (size_t)9 * slabW, gl(q - 1, c));
+        if (q == 1) put_gconst3(img, sb + (size_t)9 * slabW, gl(0, c));
+        else if (q >= 2) {
+          double g_m = gl(q - 1, c), g_0 = gl(0, c);
+          if (!(g_m > -60000.0)) g_m = -60000.0;
+          if (!(g_0 > -60000.0)) g_0 = -60000.0;
+          put_gconst3(img, sb + (size_t)9 * slabW, g_m - g_0);
+        }
       }
     }
   }
@@ -806,13 +833,7 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
   }
   int rc;
   if ((rc = ctx->w_img.ensure(img.size()))) return rc;
-  if ((rc = ctx->gconst2.ensure(gc2.size()))) return rc;
-  if ((rc = ctx->gconst_nat.ensure(gcn.size()))) return rc;
-  if ((rc = ctx->w_f32.ensure(wf.size()))) return rc;
   FB_CUDA(cudaMemcpy(ctx->w_img.p, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
-  FB_CUDA(cudaMemcpy(ctx->gconst2.p, gc2.data(), gc2.size() * sizeof(float), cudaMemcpyHostToDevice));
-  FB_CUDA(cudaMemcpy(ctx->gconst_nat.p, gcn.data(), gcn.size() * sizeof(float), cudaMemcpyHostToDevice));
-  FB_CUDA(cudaMemcpy(ctx->w_f32.p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
   ctx->n_models = n_models;
   ctx->C = C;
   // buffers that depend on n_models are (re)sized at the next fb_reserve_batch
@@ -820,7 +841,7 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
   ctx->frame_ll.release();
   ctx->avg_ll.release();
   ctx->batch_tag = -1;
-  static unsigned long long attr_set_mask = 0;
+  static std::atomic<unsigned long long> attr_set_mask{0};
   if (fb_once_per_device(attr_set_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
     FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
@@ -831,9 +852,9 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
 
 int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
   FB_CHECK_ARG(ctx->n_models > 0, "no GMMs loaded (fb_finalize_gmms)");
-  const int nch = ctx->C / FB_CHUNK_N, nst = ctx->C / FB_STAGE_N;
+  const int nst = ctx->C / FB_STAGE_N;
   int umma_grid = 0;
-  if (ctx->gmm_impl == 0) {
+  {
     GmmArgs a;
     a.a_img = ctx->a_img.p;
     a.w_img = ctx->w_img.p;
@@ -843,6 +864,7 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     a.n_models = ctx->n_models;
     a.C = ctx->C;
     a.rows_cap = ctx->rows_cap;
+    a.delta_terms = ctx->delta_terms;
     // upper bound on useful CTAs: one unit each
     const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * (ctx->gmm_shared ? 1 : ctx->n_models) * nst;
     int grid = ctx->num_sms;
@@ -851,11 +873,6 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     a.ll_out = nullptr;
     if (ctx->gmm_shared) gmm_umma_kernel<false, true><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
     else gmm_umma_kernel<false, false><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
-  } else {
-    dim3 grid(fb_div_up(ctx->total_frames, 32), ctx->n_models * nch);
-    gmm_simt_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->a_img.p, ctx->w_f32.p, ctx->gconst_nat.p,
-                                                   ctx->tables_dev->feat_scale, ctx->part.p, ctx->misc.p,
-                                                   ctx->n_models, ctx->C, ctx->rows_cap);
   }
   fb_prof_mark(ctx, 4);
   gmm_frame_kernel<<<dim3(fb_div_up(ctx->total_frames, 128), ctx->n_models), 128, 0, ctx->stream>>>(
@@ -883,6 +900,7 @@ int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag) {
   a.n_models = 1;
   a.C = ctx->C;
   a.rows_cap = ctx->rows_cap;
+  a.delta_terms = 3;
   const long long max_units = (long long)fb_div_up(ctx->total_frames, 2 * FB_TILE_M) * (ctx->C / FB_STAGE_N);
   int grid = ctx->num_sms;
   if (max_units < grid) grid = (int)max_units;

@@ -374,12 +374,17 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
   const int b = blockIdx.x;
   // blockIdx.y splits the components: a CTA buckets and accumulates only the pairs of its component range
   const int cq0 = (int)((long long)C * blockIdx.y / gridDim.y), cq1 = (int)((long long)C * (blockIdx.y + 1) / gridDim.y);
-  const int r0 = row_off[b], Tv = row_off[b + 1] - r0;
+  const int r00 = row_off[b], Tv_all = row_off[b + 1] - r00;
   const int tid = threadIdx.x;
-  if (Tv * IV_NSEL > max_pairs) {
-    if (tid == 0) atomicExch(err, 2);
-    return;
-  }
+  // Utterances longer than the shared-memory bucket capacity are processed in frame chunks, in frame order: the
+  // accumulators of a component continue from the values the previous chunk stored, so the sequence of additions is the
+  // same as for one pass (and as Kaldi's per-frame AccStats).
+  const int chunk_frames = max_pairs / IV_NSEL;
+  (void)err;
+  for (int f0 = 0; f0 < Tv_all || f0 == 0; f0 += chunk_frames) {
+  const int r0 = r00 + f0;
+  const int Tv = min(chunk_frames, Tv_all - f0);
+  __syncthreads();
   for (int c = tid; c < C; c += blockDim.x) { cnt[c] = 0; cur[c] = 0; }
   __syncthreads();
   for (int i = tid; i < Tv * IV_NSEL; i += blockDim.x) {
@@ -419,6 +424,7 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
   const int w = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
   for (int c = cq0 + w; c < cq1; c += n_warps) {
     const int n = cnt[c], o = off[c];
+    if (f0 > 0 && n == 0) continue;                           // nothing to add in this chunk
     // rank sort by frame index (frame indices within a bucket are distinct)
     for (int i = lane; i < n; i += 32) {
       const unsigned short t = lt[o + i];
@@ -428,7 +434,13 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
       lq[o + rank] = lp[o + i];
     }
     __syncwarp();
+    double *xo = Xs + ((size_t)b * C + c) * FB_DIM;
     double g = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0;
+    if (f0 > 0) {
+      g = gamma[(size_t)b * C + c];
+      x0 = xo[lane]; x1 = xo[lane + 32];
+      if (lane < 8) x2 = xo[lane + 64];
+    }
     for (int i = 0; i < n; ++i) {
       const double p = (double)lq[o + i];
       const float *xr = feats + (size_t)(r0 + ls[o + i]) * FB_DIM;
@@ -437,11 +449,11 @@ ivec_stats_kernel(const float *__restrict__ feats, const int *__restrict__ gsel,
       x1 += p * (double)xr[lane + 32];
       if (lane < 8) x2 += p * (double)xr[lane + 64];
     }
-    double *xo = Xs + ((size_t)b * C + c) * FB_DIM;
     xo[lane] = x0;
     xo[lane + 32] = x1;
     if (lane < 8) xo[lane + 64] = x2;
     if (lane == 0) gamma[(size_t)b * C + c] = g;
+  }
   }
 }
 
@@ -1248,15 +1260,14 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
         ctx->vrank.p, ctx->row_off.p, B, v->C, n_chunks, v->min_post, v->post.p, done_flag);
   }
   fb_prof_mark(ctx, 9);
-  const int max_pairs = ctx->max_frames * IV_NSEL;
+  // bucket capacity: the longest utterance, or as many frames as fit in shared memory (longer utterances go in chunks)
+  const size_t smem_fixed = (size_t)(3 * v->C + 1) * sizeof(int) + 2 * sizeof(unsigned short) + 16;
+  const int cap_frames = (int)((220 * 1024 - smem_fixed) / (IV_NSEL * 12));
+  FB_CHECK_ARG(cap_frames >= 16, "too many UBM components for the i-vector statistics kernel");
+  const int max_pairs = (ctx->max_frames < cap_frames ? ctx->max_frames : cap_frames) * IV_NSEL;
   const size_t smem_stats = (size_t)(3 * v->C + 1) * sizeof(int) + (size_t)(2 * max_pairs + 2) * sizeof(unsigned short) +
                             (size_t)2 * max_pairs * sizeof(float) + 16;
-  if (smem_stats > 220 * 1024) {
-    fb_set_error("utterance of %d frames is too long for the i-vector statistics kernel (limit ~%d frames)", ctx->max_frames,
-                 (int)((220 * 1024 - 3 * v->C * 4) / (IV_NSEL * 12)));
-    return FB_ERR_UNSUPPORTED;
-  }
-  static unsigned long long attr_mask = 0;
+  static std::atomic<unsigned long long> attr_mask{0};
   if (fb_once_per_device(attr_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(ivec_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   }
@@ -1273,7 +1284,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
                                                                                    v->n_packed, v->quad.p, done_flag);
   fb_prof_mark(ctx, 12);
   const size_t smem_solve = (2 * (size_t)v->R + ((size_t)v->R + 2) * IV_PSTRIDE) * sizeof(double);
-  static unsigned long long attr_solve_mask = 0;
+  static std::atomic<unsigned long long> attr_solve_mask{0};
   if (fb_once_per_device(attr_solve_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(ivec_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
@@ -1306,20 +1317,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   return FB_OK;
 }
 
-static int iv_check(fb_ctx *ctx) {
-  int misc[3];
-  FB_CUDA(cudaMemcpyAsync(misc, ctx->misc.p, sizeof(misc), cudaMemcpyDeviceToHost, ctx->stream));
-  FB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (misc[1] != 0) {
-    const int zero = 0;
-    cudaMemcpy(ctx->misc.p + 1, &zero, sizeof(int), cudaMemcpyHostToDevice);
-    if (misc[1] == 2) fb_set_error("utterance too long for the i-vector statistics kernel");
-    else if (misc[1] == 3) fb_set_error("i-vector posterior precision matrix is not positive definite");
-    else { fb_set_error("utterance %d has no voiced frames", misc[1] - 16); return FB_ERR_NO_VOICED; }
-    return FB_ERR_STATE;
-  }
-  return FB_OK;
-}
+static int iv_check(fb_ctx *ctx) { return fb_check_device_error(ctx); }
 
 extern "C" int fb_score_ivector_host(fb_ctx *ctx, const int16_t *wave, const int64_t *offsets, int B, double *out_scores,
                                      float *out_ivectors) {
@@ -1344,6 +1342,30 @@ extern "C" int fb_score_ivector_host(fb_ctx *ctx, const int16_t *wave, const int
   if (out_ivectors)
     FB_CUDA(cudaMemcpyAsync(out_ivectors, v->ivec.p, (size_t)B * v->R * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   return iv_check(ctx);
+}
+
+extern "C" int fb_get_ivector_stats(fb_ctx *ctx, int b, double *gamma_host, double *x_host, double *lin_host, double *quad_host) {
+  FB_CHECK_ARG(ctx && ctx->iv && b >= 0 && b < ctx->B, "bad argument");
+  FbIvector *v = ctx->iv;
+  FB_CHECK_ARG(v->gamma.p && v->quad.p, "no i-vector batch has been scored");
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (gamma_host) FB_CUDA(cudaMemcpy(gamma_host, v->gamma.p + (size_t)b * v->C, v->C * sizeof(double), cudaMemcpyDeviceToHost));
+  if (x_host)
+    FB_CUDA(cudaMemcpy(x_host, v->Xs.p + (size_t)b * v->C * FB_DIM, (size_t)v->C * FB_DIM * sizeof(double), cudaMemcpyDeviceToHost));
+  if (quad_host)
+    FB_CUDA(cudaMemcpy(quad_host, v->quad.p + (size_t)b * v->n_packed, (size_t)v->n_packed * sizeof(double), cudaMemcpyDeviceToHost));
+  if (lin_host) {
+    std::vector<double> part((size_t)v->n_splits * v->R);
+    for (int s = 0; s < v->n_splits; ++s)
+      FB_CUDA(cudaMemcpy(part.data() + (size_t)s * v->R, v->lin_part.p + ((size_t)s * ctx->B + b) * v->R, v->R * sizeof(double),
+                         cudaMemcpyDeviceToHost));
+    for (int r = 0; r < v->R; ++r) {
+      double acc = 0.0;
+      for (int s = 0; s < v->n_splits; ++s) acc += part[(size_t)s * v->R + r];
+      lin_host[r] = acc;
+    }
+  }
+  return FB_OK;
 }
 
 extern "C" int fb_get_posteriors(fb_ctx *ctx, int32_t *gsel_host, float *post_host, int64_t capacity_rows) {

@@ -82,12 +82,11 @@ perturb_kernel(FbNesDev st, int16_t *__restrict__ wave, int64_t stride, int phil
                     (uint32_t)st.seed, (uint32_t)(st.seed >> 32), r);
       box_muller(r[0], r[1], z[0], z[1]);
       box_muller(r[2], r[3], z[2], z[3]);
-      double *np_ = st.noise + (int64_t)j * st.N + n0;
-      if (vec) {                                      // one full 32-byte sector per lane
-        reinterpret_cast<double2 *>(np_)[0] = make_double2(z[0], z[1]);
-        reinterpret_cast<double2 *>(np_)[1] = make_double2(z[2], z[3]);
+      float *np_ = st.noise32 + (int64_t)j * st.N + n0;      // the deviates are float32 values: stored exactly
+      if (vec) {
+        *reinterpret_cast<float4 *>(np_) = make_float4((float)z[0], (float)z[1], (float)z[2], (float)z[3]);
       } else {
-        for (int i = 0; i < nv; ++i) np_[i] = z[i];
+        for (int i = 0; i < nv; ++i) np_[i] = (float)z[i];
       }
     } else {
       for (int i = 0; i < nv; ++i) z[i] = st.noise[(int64_t)j * st.N + n0 + i];
@@ -268,11 +267,11 @@ __global__ void nes_zero_red_kernel(FbNesDev st) {
 // mode 2: red[n] holds the all-reduced sum -> update.          mode 3: estimate only -> gest (get_grad)
 // ------------------------------------------------------------------------------------------------
 struct ColGetter {
-  const double *noise; const double *loss; int64_t N; int64_t n; int S2;
+  const double *noise; const float *noise32; const double *loss; int64_t N; int64_t n; int S2;
+  __device__ double z(int j) const { return noise32 ? (double)noise32[(int64_t)j * N + n] : noise[(int64_t)j * N + n]; }
   __device__ double operator()(int i) const {
     // column i of `loss.flatten() * noise[:, 1:]` for row n (FAKEBOB.py:244)
-    return (i < S2) ? __dmul_rn(loss[1 + i], noise[(int64_t)i * N + n])
-                    : __dmul_rn(loss[1 + i], -noise[(int64_t)(i - S2) * N + n]);
+    return (i < S2) ? __dmul_rn(loss[1 + i], z(i)) : __dmul_rn(loss[1 + i], -z(i - S2));
   }
 };
 
@@ -285,13 +284,14 @@ nes_update_kernel(FbNesDev st, int mode, int use_state_lr, double lr_arg) {
     const double *loss = st.red + st.N;
     double g;
     if (mode == 0 || mode == 3) {
-      ColGetter get{st.noise, loss, st.N, n, st.pairs_total};
+      ColGetter get{st.noise, st.noise32, loss, st.N, n, st.pairs_total};
       const double sum = np_pairwise(get, 0, st.S);
       g = __ddiv_rn(__ddiv_rn(sum, (double)st.S), st.sigma);
     } else if (mode == 1) {
       double acc = 0.0;
+      ColGetter get{st.noise, st.noise32, loss, st.N, n, st.pairs_total};
       for (int j = 0; j < st.pairs_local; ++j) {
-        const double z = st.noise[(int64_t)j * st.N + n];
+        const double z = get.z(j);
         acc = __dadd_rn(acc, __dmul_rn(loss[1 + st.pair0 + j], z));
         acc = __dadd_rn(acc, __dmul_rn(loss[1 + st.pairs_total + st.pair0 + j], -z));
       }
@@ -336,7 +336,7 @@ nes_update8_kernel(FbNesDev st, int mode) {
   const int64_t nn = valid ? n : st.N - 1;
   const double *loss = st.red + st.N;
   const int S = st.S, S2 = st.pairs_total;
-  ColGetter get{st.noise, loss, st.N, nn, S2};
+  ColGetter get{st.noise, st.noise32, loss, st.N, nn, S2};
   const int full = S - (S % 8);
   double r = get(c);
   for (int i = 8 + c; i < full; i += 8) r = __dadd_rn(r, get(i));
@@ -393,6 +393,13 @@ __global__ void nes_init_kernel(FbNesDev st) {
 // ------------------------------------------------------------------------------------------------
 // The batch workspace is shared with the plain score() entry points; re-establish the NES layout when
 // someone else used it, and drop the captured graph if any buffer was reallocated meanwhile.
+static void nes_drop_graph(FbNes *s) {
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  if (s->graph) cudaGraphDestroy(s->graph);
+  s->graph_exec = nullptr;
+  s->graph = nullptr;
+}
+
 static int nes_claim_batch(fb_ctx *ctx) {
   FbNes *s = ctx->nes;
   int rc;
@@ -404,33 +411,22 @@ static int nes_claim_batch(fb_ctx *ctx) {
   }
   if (ctx->arch == 1 && ctx->iv)
     if ((rc = fb_ivector_reserve(ctx))) return rc;       // before any graph capture
-  if (s->graph_exec && s->graph_epoch != fb_alloc_epoch()) {
-    cudaGraphExecDestroy(s->graph_exec);
-    cudaGraphDestroy(s->graph);
-    s->graph_exec = nullptr;
-    s->graph = nullptr;
-  }
+  if (s->graph_exec && (s->graph_epoch != fb_alloc_epoch() || s->graph_arch != ctx->arch ||
+                        memcmp(&s->graph_dev, &s->dev, sizeof(FbNesDev)) != 0))
+    nes_drop_graph(s);
   return FB_OK;
 }
 
-static void nes_free(FbNes *s) {
-  if (!s) return;
-  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-  if (s->graph) cudaGraphDestroy(s->graph);
-  cudaFree(s->f64_pool);
-  cudaFree(s->noise);
-  cudaFree(s->flags);
-  cudaFree(s->dist_bits);
-  delete s;
-}
-
 void fb_nes_destroy(fb_ctx *ctx) {
-  nes_free(ctx->nes);
+  FbNes *s = ctx->nes;
+  if (!s) return;
+  nes_drop_graph(s);
+  s->f64_pool.release(); s->noise64.release(); s->noise32.release(); s->flags.release(); s->dist_bits.release();
+  delete s;
   ctx->nes = nullptr;
 }
 
 static FbNesDev nes_dev(const FbNes *s) { return s->dev; }
-static int nes_claim_batch(fb_ctx *ctx);
 
 extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *audio_host, int64_t n_samples) {
   FB_CHECK_ARG(ctx && p && audio_host, "NULL argument");
@@ -455,15 +451,19 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   }
   if (p->task == FB_TASK_CSI) FB_CHECK_ARG(p->z_norm_means && p->z_norm_stds, "CSI needs z-norm statistics");
   FB_CUDA(cudaSetDevice(ctx->device));
-  fb_nes_destroy(ctx);
-  FbNes *s = new FbNes();
-  ctx->nes = s;
+  if (!ctx->nes) ctx->nes = new FbNes();
+  FbNes *s = ctx->nes;
   s->p = *p;
+  s->p.z_norm_means = s->p.z_norm_stds = nullptr;     // caller-owned host arrays: copied to the device below, not kept
   s->N = n_samples;
+  s->enqueued = 0;
   const int pairs_total = p->samples_per_draw / 2;
   const int S = 2 * pairs_total;
   int rank = 0, world = 1;
   fb_comm_info(ctx, &rank, &world);
+  // floor partition (sharding.pair_range): when the pairs do not divide evenly the LOW ranks get the smaller share, so
+  // rank 0, which also scores the clean audio, never holds more audios than the largest rank
+  // (25 pairs on 8 ranks: 3,3,3,3,3,3,3,4 pairs -> 7,6,6,6,6,6,6,8 audios).
   const int p0 = (int)((int64_t)pairs_total * rank / world), p1 = (int)((int64_t)pairs_total * (rank + 1) / world);
   s->pairs_local = p1 - p0;
   s->pair0 = p0;
@@ -478,10 +478,21 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   const size_t red_pad = (red_n + 7) & ~(size_t)7;
   const size_t log_n = (size_t)(p->max_iter + 1) * (4 + K);
   const size_t pool_n = 6 * N + red_pad + 2 * K + 128 + log_n + 8;
-  FB_CUDA(cudaMalloc(&s->f64_pool, pool_n * sizeof(double)));
-  FB_CUDA(cudaMemsetAsync(s->f64_pool, 0, pool_n * sizeof(double), ctx->stream));
-  double *q = s->f64_pool;
+  const bool philox = (p->rng == FB_RNG_PHILOX);
+  const size_t noise_n = (size_t)(s->pairs_local > 0 ? s->pairs_local : 1) * N;
+  int rc;
+  if ((rc = s->f64_pool.ensure(pool_n))) return rc;
+  if (philox) { if ((rc = s->noise32.ensure(noise_n))) return rc; }
+  else { if ((rc = s->noise64.ensure(noise_n))) return rc; }
+  if ((rc = s->flags.ensure(8 + 16))) return rc;
+  if ((rc = s->dist_bits.ensure((size_t)p->max_iter + 2))) return rc;
+  // everything except the six state vectors (nes_init_kernel / the audio copy write those) starts from zero
+  FB_CUDA(cudaMemsetAsync(s->f64_pool.p + 4 * N, 0, (pool_n - 4 * N) * sizeof(double), ctx->stream));
+  FB_CUDA(cudaMemsetAsync(s->flags.p, 0, (8 + 16) * sizeof(unsigned long long), ctx->stream));
+  FB_CUDA(cudaMemsetAsync(s->dist_bits.p, 0, ((size_t)p->max_iter + 2) * sizeof(unsigned long long), ctx->stream));
+  double *q = s->f64_pool.p;
   FbNesDev &d = s->dev;
+  memset(&d, 0, sizeof(d));                            // padding bytes too: the struct is compared to decide graph reuse
   d.audio = q; q += N; d.adver = q; q += N; d.lower = q; q += N; d.upper = q; q += N; d.grad = q; q += N; d.gest = q; q += N;
   d.red = q; q += red_pad;
   d.zmean = q; q += K; d.zstd = q; q += K;
@@ -489,15 +500,11 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   d.log = q; q += log_n;
   d.threshold = q; q += 8;
   s->red_count = red_n;
-  FB_CUDA(cudaMalloc(&s->noise, (size_t)(s->pairs_local > 0 ? s->pairs_local : 1) * N * sizeof(double)));
-  FB_CUDA(cudaMalloc(&s->flags, 16 * sizeof(int) + 16 * sizeof(unsigned long long)));
-  FB_CUDA(cudaMemsetAsync(s->flags, 0, 16 * sizeof(int) + 16 * sizeof(unsigned long long), ctx->stream));
-  FB_CUDA(cudaMalloc(&s->dist_bits, (size_t)(p->max_iter + 2) * sizeof(unsigned long long)));
-  FB_CUDA(cudaMemsetAsync(s->dist_bits, 0, (size_t)(p->max_iter + 2) * sizeof(unsigned long long), ctx->stream));
-  d.noise = s->noise;
-  d.flags = s->flags;
-  d.state_u64 = reinterpret_cast<unsigned long long *>(s->flags + 16);
-  d.dist_bits = s->dist_bits;
+  d.noise = philox ? nullptr : s->noise64.p;
+  d.noise32 = philox ? s->noise32.p : nullptr;
+  d.flags = reinterpret_cast<int *>(s->flags.p);
+  d.state_u64 = s->flags.p + 8;
+  d.dist_bits = s->dist_bits.p;
   d.N = n_samples; d.S = S; d.K = K; d.pairs_total = pairs_total; d.pairs_local = s->pairs_local; d.pair0 = p0;
   d.B_local = s->B_local; d.has_clean = s->has_clean ? 1 : 0;
   d.znorm = (iv || p->task == FB_TASK_CSI) ? 1 : 0;
@@ -517,13 +524,14 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   FB_CUDA(cudaMemcpyAsync(d.state_u64, &p->draw_base, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
   nes_init_kernel<<<fb_div_up(n_samples, 256), 256, 0, ctx->stream>>>(d);
   FB_CUDA(cudaGetLastError());
-  // batch layout: B_local utterances of n_samples each, back to back
+  // batch layout: B_local utterances of n_samples each, back to back.  Always re-established: the previous session (or a
+  // score() call) may have left the shared batch workspace laid out for another length or batch size.
   s->offsets.resize(s->B_local + 1);
   for (int b = 0; b <= s->B_local; ++b) s->offsets[b] = (int64_t)b * n_samples;
-  int rc;
   if ((rc = fb_prepare_tables(ctx))) return rc;
+  ctx->batch_tag = -1;
   if ((rc = nes_claim_batch(ctx))) return rc;
-  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));        // the host arrays (audio, z-norm, locals above) may go away now
   return FB_OK;
 }
 
@@ -593,7 +601,7 @@ extern "C" int fb_nes_run(fb_ctx *ctx, int n_iters, const double *noise_host) {
     if (host_rng) {
       // pair-major (S/2, N) float64 block for this iteration; this rank keeps its own pairs
       const double *src = noise_host + (size_t)i * per_iter + (size_t)s->pair0 * s->N;
-      FB_CUDA(cudaMemcpyAsync(s->noise, src, (size_t)s->pairs_local * s->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      FB_CUDA(cudaMemcpyAsync(s->noise64.p, src, (size_t)s->pairs_local * s->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (no_graph || host_rng || ctx->prof_on) {
       if ((rc = nes_enqueue_iteration(ctx, 0))) return rc;
@@ -607,6 +615,8 @@ extern "C" int fb_nes_run(fb_ctx *ctx, int n_iters, const double *noise_host) {
         if (e != cudaSuccess) { fb_set_error("graph capture failed: %s", cudaGetErrorString(e)); return FB_ERR_CUDA; }
         FB_CUDA(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
         s->graph_epoch = fb_alloc_epoch();
+        s->graph_dev = s->dev;
+        s->graph_arch = ctx->arch;
         s->launches_per_iter = ctx->launches - before;
         ctx->launches = before;
       }
@@ -623,13 +633,10 @@ extern "C" int fb_nes_status(fb_ctx *ctx, int *iters_done, int *stopped) {
   int h[4];
   int err[2] = {0, 0};
   // both read-backs ride the stream, one host wait for the pair
-  FB_CUDA(cudaMemcpyAsync(h, ctx->nes->flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(cudaMemcpyAsync(h, ctx->nes->dev.flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   FB_CUDA(cudaMemcpyAsync(err, ctx->misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (err[0] != 0) {
-    fb_set_error("NES batch failed on device (code %d: >=16 utterance without voiced frames, 2 utterance too long, 3 matrix not SPD)", err[0]);
-    return FB_ERR_NO_VOICED;
-  }
+  if (err[0] != 0) return fb_map_device_error(ctx, err[0]);
   if (iters_done) *iters_done = h[1];
   if (stopped) *stopped = h[0];
   return FB_OK;
@@ -676,7 +683,7 @@ extern "C" int fb_nes_get_grad(fb_ctx *ctx, const double *noise_host, double *fi
   FB_CHECK_ARG(!host_rng || noise_host, "rng = HOST needs noise_host");
   FB_CUDA(cudaSetDevice(ctx->device));
   if (host_rng)
-    FB_CUDA(cudaMemcpyAsync(s->noise, noise_host, (size_t)s->pairs_local * s->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(s->noise64.p, noise_host, (size_t)s->pairs_local * s->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   int rc;
   if ((rc = nes_claim_batch(ctx))) return rc;
   if ((rc = nes_enqueue_iteration(ctx, 1))) return rc;
@@ -686,9 +693,7 @@ extern "C" int fb_nes_get_grad(fb_ctx *ctx, const double *noise_host, double *fi
   if (grad_host)
     FB_CUDA(cudaMemcpyAsync(grad_host, s->dev.gest, s->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   FB_CUDA(cudaStreamSynchronize(ctx->stream));
-  int err = 0;
-  FB_CUDA(cudaMemcpy(&err, ctx->misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err != 0) { fb_set_error("NES batch failed on device (code %d)", err); return FB_ERR_NO_VOICED; }
+  if ((rc = fb_check_device_error(ctx))) return rc;
   if (adver_loss) *adver_loss = tail[0];
   if (final_loss) {
     // np.mean(loss[1:]) in numpy's pairwise order, on the host

@@ -10,7 +10,8 @@ struct FbNesDev {
   double *state_f64;   // [0] lr, [8..8+L) plateau window
   double *log;         // [max_iter+1][4+K]
   double *threshold;   // [0] theta (device-resident so a captured graph sees updates)
-  double *noise;       // [pairs_local][N]
+  double *noise;       // [pairs_local][N] float64: host-supplied numpy noise (rng = HOST)
+  float *noise32;      // [pairs_local][N] float32: device Philox noise (the Box-Muller deviates are float32 values), else NULL
   int *flags;          // [0] stopped, [1] iterations done, [2] stop iteration, [3] plateau window fill
   unsigned long long *state_u64;   // [0] Philox draw counter
   unsigned long long *dist_bits;   // [iter] L-inf distance before iteration `iter` (as double bits)
@@ -21,21 +22,27 @@ struct FbNesDev {
   unsigned long long seed;
 };
 
+// One per context, created by the first fb_nes_init and reused by every later session: the device buffers only grow
+// (no cudaMalloc / cudaFree per attack), and the captured iteration graph is kept while the kernel arguments it baked in
+// (buffer addresses, sizes, hyper-parameters) are unchanged.
 struct FbNes {
   fb_nes_params p;
   FbNesDev dev;
   int64_t N = 0;
   int pairs_local = 0, pair0 = 0, B_local = 0, rank = 0, world = 1;
   bool has_clean = true;
-  double *f64_pool = nullptr;
-  double *noise = nullptr;
-  int *flags = nullptr;
-  unsigned long long *dist_bits = nullptr;
+  DevBuf<double> f64_pool;
+  DevBuf<double> noise64;
+  DevBuf<float> noise32;
+  DevBuf<unsigned long long> flags;       // 8 x u64 holding 16 ints, then 16 u64 counters
+  DevBuf<unsigned long long> dist_bits;
   size_t red_count = 0;
   int enqueued = 0;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_epoch = 0;
+  FbNesDev graph_dev;                     // the arguments the captured graph was built with
+  int graph_arch = -1;
   int64_t launches_per_iter = 0;
   std::vector<int64_t> offsets;
 };

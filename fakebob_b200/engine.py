@@ -48,8 +48,10 @@ def _ptr(a):
 class GmmEngine:
     """Resident diagonal GMMs + front-end on one B200."""
 
-    def __init__(self, gmm_params, feat_cfg=None, device=None):
-        """gmm_params: list of dicts(weights, means_invvars, inv_vars, gconsts) in scoring order."""
+    def __init__(self, gmm_params, feat_cfg=None, device=None, delta_terms=None):
+        """gmm_params: list of dicts(weights, means_invvars, inv_vars, gconsts) in scoring order.
+        delta_terms: fp16 product terms of the (slot m - slot 0) part of the contraction when all slots share their
+        variances -- 1, 2, 3, or None / 0 for the automatic choice (env FAKEBOB_GMM_DELTA_TERMS overrides None)."""
         self.lib = _lib.load()
         self.device = default_device() if device is None else device
         self.cfg = feat_cfg or FeatureConfig()
@@ -71,13 +73,16 @@ class GmmEngine:
             gc = np.ascontiguousarray(g["gconsts"], dtype=np.float32)
             Cn, D = miv.shape
             _lib.check(self.lib.fb_load_diag_gmm(self.h, slot, _ptr(w), _ptr(miv), _ptr(iv), _ptr(gc), Cn, D))
+        if delta_terms is None:
+            delta_terms = int(os.environ.get("FAKEBOB_GMM_DELTA_TERMS", "0"))
+        _lib.check(self.lib.fb_set_gmm_delta_terms(self.h, int(delta_terms)))
         _lib.check(self.lib.fb_finalize_gmms(self.h, self.n_models))
         self._nes_keep = None
         self._last_B = 0
 
     @classmethod
-    def from_files(cls, paths, feat_cfg=None, device=None):
-        return cls([kaldi_io.read_diag_gmm(p) for p in paths], feat_cfg=feat_cfg, device=device)
+    def from_files(cls, paths, feat_cfg=None, device=None, delta_terms=None):
+        return cls([kaldi_io.read_diag_gmm(p) for p in paths], feat_cfg=feat_cfg, device=device, delta_terms=delta_terms)
 
     def close(self):
         if getattr(self, "h", None):
@@ -132,8 +137,16 @@ class GmmEngine:
     def set_debug(self, on=True):
         _lib.check(self.lib.fb_set_debug(self.h, 1 if on else 0))
 
-    def set_gmm_impl(self, impl):
-        _lib.check(self.lib.fb_set_gmm_impl(self.h, {"umma": 0, "tcgen05": 0, "simt": 1}.get(impl, impl)))
+    def gmm_info(self):
+        """-> dict(shared_variances, delta_terms, err_estimate) of the resident model image."""
+        sh, dt, e = C.c_int(0), C.c_int(0), C.c_double(0)
+        _lib.check(self.lib.fb_get_gmm_info(self.h, C.byref(sh), C.byref(dt), C.byref(e)))
+        return {"shared_variances": bool(sh.value), "delta_terms": dt.value, "err_estimate": e.value}
+
+    def set_delta_terms(self, terms):
+        """Rebuild the resident model image with another number of difference terms (0 = automatic)."""
+        _lib.check(self.lib.fb_set_gmm_delta_terms(self.h, int(terms)))
+        _lib.check(self.lib.fb_finalize_gmms(self.h, self.n_models))
 
     def last_stages(self):
         """Per-stage outputs of the last score call (parity tests): dict(frames, voiced, mfcc, vad, feats, frame_ll)."""
@@ -308,6 +321,7 @@ class IvectorEngine(GmmEngine):
         ic = np.ascontiguousarray(fg["inv_covars"], dtype=np.float32)
         gc = np.ascontiguousarray(fg["gconsts"], dtype=np.float32)
         Cn, D = mic.shape
+        self._C = Cn
         _lib.check(self.lib.fb_load_full_gmm(self.h, _ptr(w), _ptr(mic), _ptr(ic), _ptr(gc), Cn, D))
         ie = kaldi_io.read_ivector_extractor(os.path.join(pre, "final.ie"))
         if ie["w"].size:
@@ -357,6 +371,14 @@ class IvectorEngine(GmmEngine):
         _lib.check(self.lib.fb_score_ivector_host(self.h, _ptr(wave), _ptr(offsets), B, _ptr(out), _ptr(iv) if iv is not None else None))
         self._last_B = B
         return (out, iv) if want_ivectors else out
+
+    def stats(self, b):
+        """Intermediate results of utterance b of the last batch (parity tests):
+        dict(gamma (C,), X (C,72), lin (R,), quad (R(R+1)/2,) packed lower triangle), float64."""
+        Cn = self._C
+        out = {"gamma": np.empty(Cn), "X": np.empty((Cn, 72)), "lin": np.empty(self.R), "quad": np.empty(self.R * (self.R + 1) // 2)}
+        _lib.check(self.lib.fb_get_ivector_stats(self.h, int(b), _ptr(out["gamma"]), _ptr(out["X"]), _ptr(out["lin"]), _ptr(out["quad"])))
+        return out
 
     def posteriors(self):
         """Gaussian selection and pruned posteriors of the last batch: (rows, 20) int32 / float32."""

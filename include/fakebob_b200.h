@@ -35,6 +35,8 @@ typedef struct fb_ctx fb_ctx;
 #define FB_ERR_NO_VOICED   -4   /* an utterance has zero voiced frames (Kaldi would drop it) */
 #define FB_ERR_NCCL        -5
 #define FB_ERR_UNSUPPORTED -6
+#define FB_ERR_TOO_LONG    -7   /* an utterance exceeds a kernel's per-utterance capacity */
+#define FB_ERR_NOT_SPD     -8   /* i-vector posterior precision (quad + I) is not positive definite */
 
 const char *fb_last_error(void);
 int  fb_version(void);
@@ -69,8 +71,17 @@ int fb_set_feature_config(fb_ctx *ctx, const fb_feat_config *cfg);
 int fb_load_diag_gmm(fb_ctx *ctx, int slot, const float *weights, const float *means_invvars,
                      const float *inv_vars, const float *gconsts, int C, int D);
 int fb_finalize_gmms(fb_ctx *ctx, int n_models);
-/* 0 = tcgen05 tensor-core kernel (default), 1 = fp32 CUDA-core cross-check kernel. */
-int fb_set_gmm_impl(fb_ctx *ctx, int impl);
+/* Number of fp16 product terms used for the speaker-minus-slot-0 part of the contraction when all slots share their
+ * inverse variances (MAP mean-only adaptation, build_spk_models.py:170):  ll_m = ll_0 + x.(w_m - w_0) + (g_m - g_0).
+ * Slot 0 and the x^2 term always use the full three-term split (hi.hi + lo.hi + hi.lo, ~22 bits per operand).
+ * 3 = the same for the difference (bit-for-bit the fp32-class result), 2 = x_hi.(dw_hi + dw_lo), 1 = x_hi.dw_hi.
+ * 0 (default) = choose from the size of the differences so that the expected score deviation stays below
+ * the 1e-4 the reference's own 7-significant-digit text scores resolve (gmm_ubm_kaldiHelper.py:204-208).
+ * Call before fb_finalize_gmms. */
+int fb_set_gmm_delta_terms(fb_ctx *ctx, int terms);
+/* After fb_finalize_gmms: *shared_variances = 1 when the difference formulation is in use, *delta_terms = the number of
+ * product terms in effect, *err_estimate = the predicted per-frame error of a one-term difference product (any may be NULL). */
+int fb_get_gmm_info(fb_ctx *ctx, int *shared_variances, int *delta_terms, double *err_estimate);
 
 /* ---- batch scoring: serves gmm_{CSI,OSI,SV}.score() --------------------------------
  * Replaces: gmm_ubm_kaldiHelper.score() (gmm_ubm_kaldiHelper.py:270-291): write_audio, data_prepare,
@@ -109,6 +120,10 @@ int fb_set_enrolled_ivectors(fb_ctx *ctx, const float *enrolled, int K);
  * ivector-plda-scoring prints), or NULL; out_ivectors[b * R + r] = raw i-vectors (what ivector-extract writes), or NULL. */
 int fb_score_ivector_host(fb_ctx *ctx, const int16_t *wave, const int64_t *offsets, int B, double *out_scores,
                           float *out_ivectors);
+/* Intermediate results of utterance b of the last i-vector batch (parity tests): gamma [C], X [C x 72] (Baum-Welch
+ * statistics), lin [R] (before the prior offset), quad [R(R+1)/2] (packed lower triangle, row-major, before + I);
+ * float64, any may be NULL. */
+int fb_get_ivector_stats(fb_ctx *ctx, int b, double *gamma_host, double *x_host, double *lin_host, double *quad_host);
 /* Gaussian selection and pruned posteriors of the last i-vector batch: [rows][20] each; returns rows. */
 int fb_get_posteriors(fb_ctx *ctx, int32_t *gsel_host, float *post_host, int64_t capacity_rows);
 

@@ -13,6 +13,12 @@ TOL_FEAT = 2e-3
 TOL_FRAME_LL = 2e-3    # absolute, per-frame log-likelihood of magnitude ~100
 TOL_AVG_LL = 5e-4      # absolute, per-utterance average log-likelihood
 TOL_SCORE = 5e-4       # absolute, LLR score (difference of two averages)
+# Default (automatic) number of difference terms: speaker slots are scored as slot 0 + x.(w_m - w_0) with ONE fp16 product
+# when the MAP offsets are small (fb_set_gmm_delta_terms).  Measured at the benchmark size (scripts/gmm_precision_study.py):
+# per-frame deviation <= 6e-3 (7e-4 rms), utterance score deviation <= 1.2e-4 -- the resolution of the reference's own
+# 7-significant-digit text scores (LL ~ -1xx.xxxx, gmm_ubm_kaldiHelper.py:204-208).
+TOL_FRAME_LL_DELTA1 = 1e-2
+TOL_SCORE_DELTA1 = 3e-4
 
 
 @pytest.fixture(scope="module")
@@ -21,6 +27,7 @@ def osi(small_tree):
     m = gmm_OSI(small_tree["root"] + "/grp-osi", small_tree["models"], small_tree["ubm"],
                 pre_model_dir=small_tree["pre_model_dir"], threshold=0.1)
     m._engine.set_debug(True)
+    m._engine.set_delta_terms(3)          # the stage-by-stage tests below check the full-precision contraction
     return m
 
 
@@ -71,19 +78,33 @@ def test_frame_loglikes_match_oracle(osi, small_oracle_models):
         assert abs(avg[0, k] - float(g.avg_loglike(X))) < TOL_AVG_LL
 
 
-def test_umma_matches_simt_cross_check(osi):
-    from fakebob_b200.engine import to_audio_list
+def test_difference_terms_against_full_precision(small_tree, small_oracle_models):
+    """Shared-variance models are scored as  ll_m = ll_0 + x.(w_m - w_0) + (g_m - g_0).  With three product terms for the
+    difference the result is the full-precision one; the automatic choice (here: one term, the MAP offsets are small)
+    must stay within the stated deviation of it and of the oracle."""
+    from fakebob_b200.engine import GmmEngine, to_audio_list
+    from oracle.scorers import OracleGmmOSI
+    ubm, spk = small_oracle_models
+    paths = [small_tree["ubm"]] + [m[2] for m in small_tree["models"]]
     lst = to_audio_list([make_audio(8, 0), make_audio(9, 2)])
-    a = osi._engine.score_avg_ll(lst)
-    fa = osi._engine.last_stages()["frame_ll"].copy()
-    osi._engine.set_gmm_impl("simt")
-    try:
-        b = osi._engine.score_avg_ll(lst)
-        fb = osi._engine.last_stages()["frame_ll"].copy()
-    finally:
-        osi._engine.set_gmm_impl("umma")
-    assert np.abs(fa - fb).max() < 1e-3
-    assert np.abs(a - b).max() < 2e-4
+    want = OracleGmmOSI(ubm, spk).score(lst)
+    res = {}
+    for terms in (3, 2, 1, 0):
+        eng = GmmEngine.from_files(paths, delta_terms=terms)
+        info = eng.gmm_info()
+        assert info["shared_variances"] and info["delta_terms"] == (terms or info["delta_terms"])
+        a = eng.score_avg_ll(lst)
+        res[terms] = (a, eng.last_stages()["frame_ll"].copy(), info)
+        eng.close()
+    a3, f3, _ = res[3]
+    assert np.abs((a3[:, 1:] - a3[:, :1]) - want).max() < TOL_SCORE
+    for terms in (2, 1, 0):
+        a, f, info = res[terms]
+        assert np.array_equal(f[0], f3[0])                         # slot 0 is always the three-term contraction
+        assert np.abs(f - f3).max() < TOL_FRAME_LL_DELTA1
+        assert np.abs((a[:, 1:] - a[:, :1]) - (a3[:, 1:] - a3[:, :1])).max() < TOL_SCORE_DELTA1
+        assert np.abs((a[:, 1:] - a[:, :1]) - want).max() < TOL_SCORE
+    assert res[0][2]["delta_terms"] in (1, 2, 3) and res[0][2]["err_estimate"] > 0
 
 
 def test_osi_scores_match_oracle(osi, small_oracle_models):

@@ -46,8 +46,7 @@ def test_attack_bit_exact_given_same_scores_numpy_rng(scorers, tmp_path, task, a
     fb = FakeBob(task, attack_type, model, rng="numpy", verbose=False, **hp)
     cp = str(tmp_path / "cp.pkl")
     adv_g, flag_g = fb.attack(audio.copy(), cp, **kw)
-    np.random.seed(99)
-    _ = np.random.randint(0, 2 ** 62)        # FakeBob draws its Philox seed from the global stream at construction
+    np.random.seed(99)                       # rng="numpy": FakeBob draws nothing at construction, same stream as the reference
     ob = OracleFakeBob(task, attack_type, model, **hp)
     adv_o, flag_o = ob.attack(audio.copy(), None, **kw)
     assert flag_g == flag_o
@@ -130,7 +129,6 @@ def test_get_grad_and_estimate_threshold(scorers):
     fb.threshold = 0.7
     fl, g, al, sc = fb.get_grad(audio)
     np.random.seed(5)
-    _ = np.random.randint(0, 2 ** 62)
     ob = OracleFakeBob("OSI", "untargeted", model, samples_per_draw=8)
     ob.threshold = 0.7
     fl2, g2, al2, sc2 = ob.get_grad(audio)
@@ -141,12 +139,47 @@ def test_get_grad_and_estimate_threshold(scorers):
     fb = FakeBob("OSI", "targeted", model, samples_per_draw=8, rng="numpy", verbose=False, max_lr=0.001)
     r1 = fb.estimate_threshold(audio)
     np.random.seed(6)
-    _ = np.random.randint(0, 2 ** 62)
     ob = OracleFakeBob("OSI", "targeted", model, samples_per_draw=8, max_lr=0.001)
     r2 = ob.estimate_threshold(audio)
     assert r1[0] == r2[0] and r1[1] == r2[1]
     assert fb.attack_type == "targeted"
     model.threshold = 0.0
+
+
+def test_back_to_back_sessions_with_different_length_and_draw(scorers):
+    """Consecutive attacks with no score() call in between (attackMain.py's loops, sharding.attack_many) on audios of
+    different length and with different samples_per_draw: every session must lay the shared batch workspace out afresh."""
+    from fakebob_b200.FAKEBOB import FakeBob
+    from oracle.nes import OracleFakeBob, PhiloxNoise
+    model = scorers["OSI"]
+    plan = [(make_audio(36, 0, n=16000), 6, 5), (make_audio(37, 1, n=24000), 10, 6), (make_audio(38, 2, n=8000), 4, 7),
+            (make_audio(39, 0, n=24000), 10, 8)]
+    got = []
+    for audio, S, seed in plan:                          # device sessions back to back, nothing else touches the context
+        fb = FakeBob("OSI", "untargeted", model, max_iter=3, samples_per_draw=S, seed=seed, verbose=False)
+        adv, flag = fb.attack(audio.copy(), None, threshold=1.0)
+        got.append((adv.copy(), flag, fb.log.copy()))
+    for (audio, S, seed), (adv, flag, log) in zip(plan, got):
+        ob = OracleFakeBob("OSI", "untargeted", model, max_iter=3, samples_per_draw=S, noise_fn=PhiloxNoise(seed))
+        adv_o, flag_o = ob.attack(audio.copy(), None, threshold=1.0)
+        assert flag == flag_o and log.shape[0] == len(ob.log)
+        assert adv.shape == adv_o.shape and np.mean(adv == adv_o) > 0.9999
+        assert np.abs(log[:, 1] - np.array([float(np.asarray(r[1]).reshape(-1)[0]) for r in ob.log])).max() < 1e-6
+
+
+def test_device_error_is_reported_once_with_its_own_code(scorers):
+    from fakebob_b200._lib import FakebobLibraryError
+    from fakebob_b200.FAKEBOB import FakeBob
+    model = scorers["SV"]
+    silent = np.zeros(16000)
+    silent[::7] = 1.0 / 32768
+    fb = FakeBob("SV", "untargeted", model, max_iter=2, samples_per_draw=4, seed=1, verbose=False, sigma=1e-9)
+    with pytest.raises(FakebobLibraryError) as ei:
+        fb.attack(silent, None, threshold=1e3)
+    assert "error -4" in str(ei.value) and "no voiced frames" in str(ei.value)
+    # the flag was cleared: an unrelated batch right after succeeds
+    ok = model.score(make_audio(33, 0, n=16000))
+    assert np.isfinite(ok)
 
 
 def test_requires_device_backed_model():
