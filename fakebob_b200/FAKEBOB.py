@@ -58,6 +58,7 @@ class FakeBob(object):
             self.seed = int(np.random.randint(0, 2 ** 62)) if self.rng == "philox" else 0
         self.verbose = (os.environ.get("FAKEBOB_VERBOSE", "1") != "0") if verbose is None else verbose
         self.iters_per_launch = max(1, int(iters_per_launch))
+        self.estimate_max_iters = 20000        # bound on the inner iterations of estimate_threshold (the reference loops forever)
         self.draws = 0                 # Philox draw counter == number of get_grad evaluations so far
         self.threshold = 0.
         self.true = None
@@ -112,7 +113,7 @@ class FakeBob(object):
         eng = self._nes_init(audio, self.max_iter)
         t_start = time.time()
         self.poll_times = [t_start - t_init]         # seconds: fb_nes_init, then one entry per polled batch of iterations
-        done, stopped, printed = 0, False, 0
+        done, stopped, printed = 0, 0, 0
         chunk = 1 if self.rng == "numpy" else self.iters_per_launch
         while not stopped and done < self.max_iter:
             k = min(chunk, self.max_iter - done)
@@ -201,6 +202,8 @@ class FakeBob(object):
         self.attack_type = UNTARGETED
         n = audio.shape[0]
         try:
+            if self.rng == "philox":
+                return self._estimate_threshold_device(audio)
             eng = self._nes_init(audio, 1)
             iter_outer, n_iters, times = 0, 0, 0.
             while True:
@@ -228,7 +231,7 @@ class FakeBob(object):
                         if self.verbose:
                             print("--- early stop at iter_inner:%d ---" % (iter_inner))
                         break
-                    noise = self._host_noise(n) if self.rng == "numpy" else None
+                    noise = self._host_noise(n)
                     loss, _, _, _ = eng.nes_get_grad(noise)
                     self.draws += 1
                     last_ls.append(loss)
@@ -248,3 +251,58 @@ class FakeBob(object):
                 iter_outer += 1
         finally:
             self.attack_type = attack_type_backup
+
+    def _estimate_threshold_device(self, audio):
+        """The search of FAKEBOB.py:76-137 with every inner iteration on the device (fb_nes_estimate_begin / fb_nes_continue):
+        the make_decisions() score of the current adversarial audio is column 0 of the iteration's own batch, so no second
+        scoring call and no host round trip per inner iteration.  Same control flow, prints and return value."""
+        eng = self._nes_init(audio, self.estimate_max_iters)
+        eng.nes_estimate_begin(self.model.threshold)
+        iter_outer, n_iters, times, rows_seen = 0, 0, 0., 0
+        chunk = self.iters_per_launch
+        while True:
+            if self.verbose:
+                print("----- iter_outer:%d, threshold:%f -----" % (iter_outer, self.threshold))
+            eng.nes_continue(self.threshold)
+            start = time.time()
+            stopped = 0
+            while not stopped:
+                eng.nes_run(chunk)
+                done, stopped = eng.nes_status()
+                if not stopped and done >= self.estimate_max_iters:
+                    raise RuntimeError("estimate_threshold: no decision after %d inner iterations" % self.estimate_max_iters)
+            rows = eng.nes_log(done)
+            elapsed = time.time() - start
+            n_new = done - rows_seen                    # inner iterations of this outer iteration, the last one is the stop test
+            per_iter = elapsed / max(n_new, 1)
+            for i in range(n_new):
+                r = rows[rows_seen + i]
+                score = self._score_row(r)
+                last = i == n_new - 1
+                if self.verbose:
+                    print("--- iter_inner:%d, dicision:%d, score: ---" % (i, self._decision(score) if (last and stopped == 2) else -1), score)
+                    if not last:
+                        print("consumption time:%f, lr:%f" % (per_iter, r[3]))
+            n_iters += n_new - 1
+            times += per_iter * (n_new - 1)
+            self.draws += n_new - 1
+            rows_seen = done
+            final = rows[done - 1]
+            score = self._score_row(final)
+            if self.task == "OSI":
+                score = np.max(score)
+            if stopped == 2:
+                if self.verbose:
+                    print("--- return at iter_outer:%d, iter_inner:%d, return thresh:%f ---" % (iter_outer, n_new - 1, score))
+                    print("cost %d iters, %fs time" % (n_iters, times))
+                return score, n_iters, times
+            if self.verbose:
+                print("--- early stop at iter_inner:%d ---" % (n_new - 1))
+            self.threshold += self.delta
+            iter_outer += 1
+
+    def _decision(self, score):
+        """make_decisions() of the scorer for one audio, from its scores (gmm_ubm_OSI.py:93-112, gmm_ubm_SV.py:81-92)."""
+        if self.task == "OSI":
+            return int(np.argmax(score)) if np.max(score) >= self.model.threshold else -1
+        return 1 if score >= self.model.threshold else -1

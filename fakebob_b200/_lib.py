@@ -70,6 +70,8 @@ _SIGS = {
     "fb_nes_read_log": (C.c_int, [_P, _P, C.c_int]),
     "fb_nes_read_adver": (C.c_int, [_P, _P, C.c_int64]),
     "fb_nes_read_grad": (C.c_int, [_P, _P, C.c_int64]),
+    "fb_nes_estimate_begin": (C.c_int, [_P, C.c_double]),
+    "fb_nes_continue": (C.c_int, [_P, C.c_double]),
     "fb_nes_get_grad": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P]),
     "fb_nes_apply_update": (C.c_int, [_P, C.c_double]),
     "fb_nes_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),

@@ -24,6 +24,13 @@ class FeatureConfig:
     preemph: float = 0.97
     cepstral_lifter: float = 22.0
     dither: float = 0.0            # Kaldi's default 1.0 is a documented non-ideal effect; off here
+    use_energy: bool = True        # Kaldi defaults below; the kernels implement exactly these values
+    raw_energy: bool = True
+    energy_floor: float = 0.0
+    window_type: str = "povey"
+    remove_dc_offset: bool = True
+    htk_compat: bool = False
+    round_to_power_of_two: bool = True
     vad_energy_threshold: float = 5.5
     vad_energy_mean_scale: float = 0.5
     vad_proportion_threshold: float = 0.12
@@ -71,6 +78,12 @@ class FeatureConfig:
             raise ValueError("snip_edges=true is not supported by the CUDA MFCC kernel")
         if self.dither != 0.0:
             raise ValueError("dither is not supported on the device path (SURVEY.md A.9)")
+        fixed = {"use_energy": True, "raw_energy": True, "energy_floor": 0.0, "window_type": "povey", "remove_dc_offset": True,
+                 "htk_compat": False, "round_to_power_of_two": True}
+        for k, want in fixed.items():
+            if getattr(self, k) != want:
+                raise ValueError("unsupported mfcc.conf option: --%s=%s (the CUDA MFCC kernel implements %s only)"
+                                 % (k.replace("_", "-"), getattr(self, k), want))
 
 
 _BOOL = {"true": True, "false": False}
@@ -91,6 +104,20 @@ def load_feature_config(pre_model_dir):
         cfg.snip_edges = _BOOL[o.get("snip-edges", "true").lower()] if "snip-edges" in o else cfg.snip_edges
         cfg.preemph = float(o.get("preemphasis-coefficient", cfg.preemph))
         cfg.cepstral_lifter = float(o.get("cepstral-lifter", cfg.cepstral_lifter))
+        cfg.dither = float(o.get("dither", cfg.dither))          # only an explicit value; Kaldi's implicit 1.0 stays off (A.9)
+        cfg.energy_floor = float(o.get("energy-floor", cfg.energy_floor))
+        cfg.window_type = o.get("window-type", cfg.window_type)
+        for key, attr in (("use-energy", "use_energy"), ("raw-energy", "raw_energy"), ("remove-dc-offset", "remove_dc_offset"),
+                          ("htk-compat", "htk_compat"), ("round-to-power-of-two", "round_to_power_of_two")):
+            if key in o:
+                setattr(cfg, attr, _BOOL[o[key].lower()])
+        known = {"sample-frequency", "frame-length", "frame-shift", "low-freq", "high-freq", "num-mel-bins", "num-ceps", "snip-edges",
+                 "preemphasis-coefficient", "cepstral-lifter", "dither", "energy-floor", "window-type", "use-energy", "raw-energy",
+                 "remove-dc-offset", "htk-compat", "round-to-power-of-two"}
+        unknown = sorted(set(o) - known)
+        if unknown:
+            import warnings
+            warnings.warn("mfcc.conf options not understood by fakebob_b200 (ignored): %s" % ", ".join(unknown))
     vad_conf = os.path.join(pre_model_dir, "conf", "vad.conf")
     if os.path.exists(vad_conf):
         o = kaldi_io.parse_conf(vad_conf)

@@ -4,6 +4,7 @@
 #include "fb_nes.cuh"
 #include "fb_ivector.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 
@@ -15,6 +16,10 @@ void fb_set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool fb_pdl_enabled() {
+  static const bool on = getenv("FB_NO_PDL") == nullptr;
+  return on;
 }
 uint64_t fb_alloc_epoch() { return g_epoch.load(); }
 void fb_bump_alloc_epoch() { g_epoch.fetch_add(1); }

@@ -27,6 +27,9 @@
 #define FB_STAGE_N     64      // W columns per smem stage
 #define FB_CHUNK_N     128     // accumulator columns per (tile, unit)
 #define FB_MAX_MODELS  32
+#ifndef FB_GMM_EPI_HALVES
+#define FB_GMM_EPI_HALVES 2    // column ranges per accumulator in the GMM epilogue (fb_gmm.cu): partials are [model][stage][range][row]
+#endif
 #define FB_MEL_MAXLEN  48
 
 void fb_set_error(const char *fmt, ...);
@@ -174,3 +177,31 @@ static inline bool fb_once_per_device(std::atomic<unsigned long long> &mask, int
   return (mask.fetch_or(bit) & bit) == 0;
 }
 static inline int fb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// Every kernel of the scoring / NES sequence is launched with the programmatic-stream-serialization attribute and starts
+// with FB_GRID_DEP_SYNC(): the next kernel's CTAs are scheduled (launch latency, prologue) while the previous kernel
+// drains, and block at griddepcontrol.wait until it has completed and flushed its memory.  The wait is executed
+// unconditionally, before any early return, so completion stays transitive along the chain.  FB_NO_PDL=1 launches plainly.
+bool fb_pdl_enabled();
+#ifdef __CUDACC__
+#define FB_GRID_DEP_SYNC()                                          \
+  do {                                                              \
+    asm volatile("griddepcontrol.wait;" ::: "memory");              \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t fb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = fb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(MFCC_WARPS * 32)
 mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_off,
             const int *__restrict__ frame_off, const FbTables *__restrict__ tb,
             float *__restrict__ mfcc, const int *__restrict__ done_flag) {
+  FB_GRID_DEP_SYNC();
   if (done_flag && *done_flag) return;
   __shared__ float2 s_buf[MFCC_WARPS][2][FFT_BUF];
   __shared__ float2 s_tw[FB_FFT_N];
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(256)
 vad_scan_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_off, const FbTables *__restrict__ tb,
                 int *__restrict__ vrank, int *__restrict__ nvoiced, int *__restrict__ row_off,
                 int *__restrict__ misc, int B, int c0_cap, const int *__restrict__ done_flag) {
+  FB_GRID_DEP_SYNC();
   if (done_flag && *done_flag) return;
   __shared__ double s_red[8];
   __shared__ int s_wtot[8];
@@ -422,6 +424,7 @@ feats_kernel(const float *__restrict__ mfcc, const int *__restrict__ frame_off, 
              const int *__restrict__ row_off, const FbTables *__restrict__ tb, __half *__restrict__ a_img,
              float *__restrict__ feats_f32, float *__restrict__ raw_global, double *__restrict__ pre_global,
              int use_smem, const int *__restrict__ done_flag) {
+  FB_GRID_DEP_SYNC();
   if (done_flag && *done_flag) return;
   extern __shared__ double s_dyn[];
   __shared__ double s_seg[FEATS_NSEG][8];
@@ -593,7 +596,7 @@ int fb_reserve_batch(fb_ctx *ctx, int B, const int64_t *offsets_host) {
   }
   if (ctx->n_models > 0) {
     const size_t nst = ctx->C / FB_STAGE_N;          // one partial slot per 64-column stage (gmm_umma_kernel segments)
-    if ((rc = ctx->part.ensure((size_t)ctx->n_models * nst * ctx->rows_cap))) return rc;
+    if ((rc = ctx->part.ensure((size_t)ctx->n_models * nst * FB_GMM_EPI_HALVES * ctx->rows_cap))) return rc;
     if ((rc = ctx->frame_ll.ensure((size_t)ctx->n_models * ctx->rows_cap))) return rc;
     if ((rc = ctx->avg_ll.ensure((size_t)B * ctx->n_models))) return rc;
   }
@@ -613,12 +616,12 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   if ((rc = fb_prepare_tables(ctx))) return rc;
   const int B = ctx->B;
   dim3 g1(fb_div_up(ctx->max_frames, MFCC_WARPS), B);
-  mfcc_kernel<<<g1, MFCC_WARPS * 32, 0, ctx->stream>>>(ctx->wave.p, ctx->wave_off.p, ctx->frame_off.p, ctx->tables_dev,
-                                                       ctx->mfcc.p, done_flag);
+  FB_CUDA(fb_launch(mfcc_kernel, g1, dim3(MFCC_WARPS * 32), 0, ctx->stream, ctx->wave.p, ctx->wave_off.p, ctx->frame_off.p,
+                    ctx->tables_dev, ctx->mfcc.p, done_flag));
   fb_prof_mark(ctx, 1);
   const int c0_cap = ctx->max_frames < 8192 ? ctx->max_frames : 8192;
-  vad_scan_kernel<<<B, 256, (size_t)c0_cap * sizeof(float), ctx->stream>>>(ctx->mfcc.p, ctx->frame_off.p, ctx->tables_dev, ctx->vrank.p,
-                                                                          ctx->nvoiced.p, ctx->row_off.p, ctx->misc.p, B, c0_cap, done_flag);
+  FB_CUDA(fb_launch(vad_scan_kernel, dim3(B), dim3(256), (size_t)c0_cap * sizeof(float), ctx->stream, ctx->mfcc.p, ctx->frame_off.p,
+                    ctx->tables_dev, ctx->vrank.p, ctx->nvoiced.p, ctx->row_off.p, ctx->misc.p, B, c0_cap, done_flag));
   fb_prof_mark(ctx, 2);
   const size_t smem = fb_feats_smem_bytes(ctx->max_frames);
   const int use_smem = smem <= FB_FEATS_SMEM_MAX;
@@ -626,10 +629,10 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   if (fb_once_per_device(configured_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(feats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_FEATS_SMEM_MAX));
   }
-  feats_kernel<<<dim3(9, B), FEATS_THREADS, use_smem ? smem : 0, ctx->stream>>>(
-      ctx->mfcc.p, ctx->frame_off.p, ctx->vrank.p, ctx->row_off.p, ctx->tables_dev, ctx->a_img.p,
-      (ctx->debug_feats || ctx->need_feats_f32) ? ctx->feats_f32.p : nullptr, use_smem ? nullptr : ctx->raw72.p,
-      use_smem ? nullptr : ctx->cmn_prefix.p, use_smem, done_flag);
+  FB_CUDA(fb_launch(feats_kernel, dim3(9, B), dim3(FEATS_THREADS), use_smem ? smem : 0, ctx->stream, ctx->mfcc.p, ctx->frame_off.p,
+                    ctx->vrank.p, ctx->row_off.p, ctx->tables_dev, ctx->a_img.p,
+                    (ctx->debug_feats || ctx->need_feats_f32) ? ctx->feats_f32.p : nullptr, use_smem ? nullptr : ctx->raw72.p,
+                    use_smem ? nullptr : ctx->cmn_prefix.p, use_smem, done_flag));
   fb_prof_mark(ctx, 3);
   ctx->launches += 3;
   FB_CUDA(cudaGetLastError());

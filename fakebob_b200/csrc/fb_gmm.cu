@@ -50,8 +50,15 @@
 #ifndef GMM_PARTS
 #define GMM_PARTS 3
 #endif
-#define GMM_THREADS 352                       // producer warp + MMA issuer (tile 0) + 8 epilogue warps + MMA issuer (tile 1)
-#define GMM_ISSUER1 10
+// Warps: 0 = bulk-copy producer, 1 / 2 = MMA issuers (tile 0 / tile 1), 3.. = epilogue.  FB_GMM_EPI_HALVES = 2: sixteen
+// epilogue warps, each owning 32 lanes x 32 of the 64 accumulator columns (the kernel is epilogue-bound once the speaker
+// slots cost 5 MMAs per job: measured 123 us with eight 64-column warps vs 72 us with the log-sum-exp compiled out; the
+// per-job work is one dependent chain -- tcgen05.ld, add, max tree, votes, exponentials -- so more warps per scheduler
+// hide its latency).  1: eight warps x 64 columns.
+#define GMM_EPI_WARP0 3
+#define GMM_EPI_COLS (FB_STAGE_N / FB_GMM_EPI_HALVES)
+#define GMM_THREADS (32 * (GMM_EPI_WARP0 + 8 * FB_GMM_EPI_HALVES))
+#define GMM_ISSUER1 2
 // Operand K layout (slabs of 8 fp16) for the hi and lo halves of A and W alike:
 //   [x 0..8][ones | gconst 9][x^2 10..18][zero 19]   (20 slabs = 10 k-blocks of K=16; each half is 5 k-blocks)
 // gconst*log2(e) sits in W's slab 9 as three fp16 terms (g_hi, g_mid, g_lo) against three 1.0 columns of A's "ones" slab,
@@ -74,8 +81,13 @@ static_assert(kSmemLaunch <= 232448, "exceeds the 227 KB per-CTA shared memory l
 // TMEM columns (all 512 used): three 64-column accumulators [0,192) used as a ring over (tile, sub-step) jobs, so the
 // MMA <-> epilogue hand-shake latency is hidden behind two jobs; A operand: tile t at 192 + 160 t: hi 80 columns, lo 80 columns
 static constexpr uint32_t kTmemAcc = 0;
+#ifdef GMM_ACC5_HACK      // TIMING EXPERIMENT ONLY (wrong numerics): five accumulators, the lo halves of A alias other columns
+static constexpr uint32_t kNumAcc = 5;
+static constexpr uint32_t kTmemA = 320;
+#else
 static constexpr uint32_t kNumAcc = 3;
 static constexpr uint32_t kTmemA = 192;
+#endif
 static constexpr uint32_t kTmemAHalfCols = FB_A_HI_SLABS * 4;                  // 80
 static constexpr uint32_t kTmemATileCols = 2 * kTmemAHalfCols;                 // 160
 static constexpr uint32_t kTmemX2Cols = FB_SLAB_X2 * 4;                        // 40: column offset of the x^2 half
@@ -185,7 +197,7 @@ static constexpr uint32_t kIdesc = (1u << 4) | ((FB_STAGE_N >> 3) << 17) | ((FB_
 struct GmmArgs {
   const __half *a_img;      // [tile][hi 19 slabs | lo 18 slabs][128][8]
   const __half *w_img;      // [model][C/64][hi 20 slabs | lo 18 slabs][64][8]
-  float2 *part;             // [model][C/64][rows_cap]: (max, sum) of the segment of 64-column stages that STARTS at that stage
+  float2 *part;             // [model][C/64][column range][rows_cap]: (max, sum) of the segment of 64-column stages that STARTS at that stage
   const int *misc;          // misc[2] = total voiced rows
   const int *done_flag;
   float *ll_out;            // STORE mode: [rows_cap][C] natural-log component log-likelihoods (Gaussian selection)
@@ -216,29 +228,39 @@ __host__ __device__ __forceinline__ SharedLayout shared_layout(int n_models, int
 // evaluated per 8-column group and only when a warp vote finds a lane that still needs them (measured on the C2 model:
 // ~75 % of the warp x 8-column groups are dead).  All eight votes are taken before the first exponential so their
 // latencies overlap.  `m` is the running row maximum, `s` the sum relative to it.
-__device__ __forceinline__ void lse_stage(const float *va, const float *vb, float &m, float &s) {
-  float gmax[8];
+#ifndef GMM_LSE_GROUP
+#define GMM_LSE_GROUP 8
+#endif
+template <int NC>
+__device__ __forceinline__ void lse_stage(const float *v, float &m, float &s) {
+  constexpr int GS = GMM_LSE_GROUP;
+  constexpr int NG = NC / GS;
+  float gmax[NG];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float *q = (k < 4) ? va + 8 * k : vb + 8 * (k - 4);
-    gmax[k] = max3(max3(q[0], q[1], q[2]), max3(q[3], q[4], q[5]), fmaxf(q[6], q[7]));
+  for (int k = 0; k < NG; ++k) {
+    const float *q = v + GS * k;
+    if constexpr (GS == 8) gmax[k] = max3(max3(q[0], q[1], q[2]), max3(q[3], q[4], q[5]), fmaxf(q[6], q[7]));
+    else gmax[k] = fmaxf(max3(q[0], q[1], q[2]), q[3]);
   }
-  const float cmax = fmaxf(max3(gmax[0], gmax[1], gmax[2]), max3(gmax[3], gmax[4], max3(gmax[5], gmax[6], gmax[7])));
+  float cmax = gmax[0];
+#pragma unroll
+  for (int k = 1; k + 1 < NG; k += 2) cmax = max3(cmax, gmax[k], gmax[k + 1]);
+  if constexpr ((NG & 1) == 0) cmax = fmaxf(cmax, gmax[NG - 1]);
   if (cmax > m) {
     s *= ex2_approx(m - cmax);
     m = cmax;
   }
   const float thr = m - 23.0f;
-  bool alive[8];
+  bool alive[NG];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) alive[k] = __any_sync(0xffffffffu, gmax[k] >= thr);
+  for (int k = 0; k < NG; ++k) alive[k] = __any_sync(0xffffffffu, gmax[k] >= thr);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < NG; ++k) {
     if (alive[k]) {
-      const float *q = (k < 4) ? va + 8 * k : vb + 8 * (k - 4);
+      const float *q = v + GS * k;
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; i += 2) {
+      for (int i = 0; i < GS; i += 2) {
         const float t0 = q[i] - m, t1 = q[i + 1] - m;
         const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
         if (t0 >= -23.0f) s0 += e0;
@@ -274,7 +296,6 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
   const long long ck_entry = clock64();
 #endif
-  if (g.done_flag && *g.done_flag) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 127u) & ~127u;
@@ -288,8 +309,27 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmemBar + 16 * kNumSlots + 32 * kNumAcc + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int M = g.misc[2];
   const int nst = g.C / FB_STAGE_N;
+  // barrier init and the TMEM allocation touch no global memory: they run while the previous kernel drains
+  if (warp == 0 && lane == 0) {
+    for (uint32_t i = 0; i < kNumSlots; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 2);          // one arrive per issuer warp
+    }
+    for (uint32_t i = 0; i < 2 * kNumAcc; ++i) {
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 4 * FB_GMM_EPI_HALVES);     // one arrive per epilogue warp of the tile that read it
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  FB_GRID_DEP_SYNC();
+  const bool skip = g.done_flag && *g.done_flag;     // NES early stop: fall through with no work (TMEM must still be freed)
+  const int M = skip ? 0 : g.misc[2];
   const int n_super = (M + 2 * FB_TILE_M - 1) / (2 * FB_TILE_M);
   // Work = the sequence of 64-column stages ordered (super-tile, [model,] stage); general mode: one model per stage,
   // shared mode: all models inside a stage.  CTA b takes the contiguous range [total b / grid, total (b+1) / grid)
@@ -301,22 +341,6 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   const int n_sub = kShared ? g.n_models + 1 : 1;                              // sub-stages (jobs per tile) per 64-column stage
   const SharedLayout SL = shared_layout(g.n_models, g.delta_terms);
 
-  if (warp == 0 && lane == 0) {
-    for (uint32_t i = 0; i < kNumSlots; ++i) {
-      mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 2);          // one arrive per issuer warp
-    }
-    for (uint32_t i = 0; i < 2 * kNumAcc; ++i) {
-      mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 4);     // one arrive per epilogue warp of the tile that read it
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -422,7 +446,11 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           if (elect_one()) {
             if ((e >> 1) == tile) {
               const uint64_t src = desc_a + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
+#ifdef GMM_ACC5_HACK
+              const uint32_t dst = tmem_base + ((e & 1) ? 432u : kTmemA + tile * kTmemAHalfCols);
+#else
               const uint32_t dst = tmem_base + kTmemA + tile * kTmemATileCols + (e & 1) * kTmemAHalfCols;
+#endif
 #pragma unroll
               for (int kb = 0; kb < FB_A_HI_SLABS / 2; ++kb) tc_cp_128x256b(dst + kb * 8, src + (uint64_t)(kb * ((2 * kSlabA) >> 4)));
               tc_commit(bar_empty + 8 * slot);
@@ -461,13 +489,21 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           if (job >= kNumAcc) STAT_WAIT(st_mma_acc, bar_acc_empty + 8 * (2 * abuf + (tile ^ 1)), ((job - kNumAcc) / (2 * kNumAcc)) & 1);
           tc_fence_after();
           if (elect_one()) {
+#ifdef GMM_ACC5_HACK
+            const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemAHalfCols + a_off;
+            const uint32_t a_lo = tmem_base + 432u + a_off;
+#else
             const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols + a_off;
             const uint32_t a_lo = a_hi + kTmemAHalfCols;
+#endif
             const uint32_t d_tmem = tmem_base + kTmemAcc + abuf * FB_STAGE_N;
             constexpr int nkb = kShared ? 5 : 10;
 #pragma unroll
             for (int part = 0; part < GMM_PARTS; ++part) {
               if (!((mask >> part) & 1u)) continue;
+#ifdef GMM_ACC5_HACK
+              if (part == 1) continue;                 // the aliased lo operand holds garbage: keep the values realistic
+#endif
               const uint32_t a_base = (part == 1) ? a_lo : a_hi;
               const uint64_t b_base = (part == 2) ? w_lo : w_hi;
 #pragma unroll
@@ -488,30 +524,33 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     if (lane == 0) { g_gmm_stats[blockIdx.x * 16 + 6 + 2 * tile] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 7 + 2 * tile] = st_mma_full + st_mma_afull + st_mma_acc; }
 #endif
   } else {
-    // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, tile = (warp - 2) / 4 =====
+    // ===== epilogue: warps 3..; TMEM lane quadrant = warp % 4; (warp - 3) / 4 = 2 * half + tile: an accumulator is read by
+    // 4 lane quadrants x FB_GMM_EPI_HALVES column ranges =====
+    constexpr int NC = GMM_EPI_COLS;
     const int quad = warp & 3;
-    const int tile = (warp - 2) >> 2;
+    const int tile = ((warp - GMM_EPI_WARP0) >> 2) & 1;
+    const int half = (warp - GMM_EPI_WARP0) >> 3;
     uint32_t job = tile;                               // this tile's jobs are tile, tile + 2, tile + 4, ...
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc + half * NC;
     float mm[kShared ? FB_MAX_MODELS : 1], ss[kShared ? FB_MAX_MODELS : 1];
     int run_item = -1;                                  // the running maxima belong to this (super[, model])
     STAT_DECL(st_epi_full);
 #ifdef GMM_STATS
     const long long st_t0 = clock64();
 #endif
-    // wait for this tile's next accumulator, pull its 64 columns of this warp's 32 lanes into registers, hand it back
-    auto fetch = [&](float (&va)[32], float (&vb)[32]) {
+    // wait for this tile's next accumulator, pull this warp's 32 lanes x NC columns into registers, hand it back
+    auto fetch = [&](float (&v)[NC]) {
       const uint32_t abuf = job % kNumAcc;
       STAT_WAIT(st_epi_full, bar_acc_full + 8 * (2 * abuf + tile), (job / (2 * kNumAcc)) & 1);
       tc_fence_after();
       const uint32_t taddr = taddr0 + abuf * FB_STAGE_N;
 #ifndef GMM_NO_LDTM
-      tc_ld32(taddr, va);
-      tc_ld32(taddr + 32, vb);
+      tc_ld32(taddr, v);
+      if constexpr (NC == 64) tc_ld32(taddr + 32, v + 32);
       tc_wait_ld();
 #else
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { va[i] = (float)(i + job); vb[i] = (float)(i - job); }
+      for (int i = 0; i < NC; ++i) v[i] = (float)(i + job);
 #endif
       tc_fence_before();
       __syncwarp();
@@ -519,15 +558,15 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       job += 2;
     };
     // The running (max, sum) of a row is kept over the whole run of consecutive stages this CTA computes for the same
-    // (rows[, model]) -- a "segment" -- so the cutoff is relative to the running maximum; one partial per segment, stored
-    // at the index of the segment's first stage.
+    // (rows[, model]) -- a "segment" -- so the cutoff is relative to the running maximum; one partial per segment and column
+    // range, stored at the index of the segment's first stage.
     const int n_run = kShared ? g.n_models : 1;
     int seg_start = 0, seg_row = 0, seg_model = 0;
     auto flush = [&]() {
       if constexpr (!kStore) {
         for (int r = 0; r < n_run; ++r) {
           const int mdl = kShared ? r : seg_model;
-          g.part[((size_t)mdl * nst + seg_start) * g.rows_cap + seg_row] = make_float2(mm[r], ss[r]);
+          g.part[(((size_t)mdl * nst + seg_start) * FB_GMM_EPI_HALVES + half) * g.rows_cap + seg_row] = make_float2(mm[r], ss[r]);
         }
       }
     };
@@ -543,59 +582,54 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         run_item = item;
         seg_start = stage; seg_row = row; seg_model = model;
       }
-      {
-        if constexpr (kShared) {
-          float qa[32], qb[32];                         // Q (x^2 term), then ll_0 = Q + T_0: the base every other slot adds to
-          fetch(qa, qb);
+      if constexpr (kShared) {
+        float q[NC];                                    // Q (x^2 term), then ll_0 = Q + T_0: the base every other slot adds to
+        fetch(q);
 #pragma unroll 1
-          for (int r = 0; r < g.n_models; ++r) {
-            float va[32], vb[32];
-            fetch(va, vb);
+        for (int r = 0; r < g.n_models; ++r) {
+          float v[NC];
+          fetch(v);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float2 t0 = __fadd2_rn(make_float2(va[i], va[i + 1]), make_float2(qa[i], qa[i + 1]));
-              const float2 t1 = __fadd2_rn(make_float2(vb[i], vb[i + 1]), make_float2(qb[i], qb[i + 1]));
-              va[i] = t0.x; va[i + 1] = t0.y; vb[i] = t1.x; vb[i + 1] = t1.y;
-            }
-            if (r == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) { qa[i] = va[i]; qb[i] = vb[i]; }
-            }
-            float m = mm[r], sacc = ss[r];
-#ifndef GMM_NO_LSE
-            lse_stage(va, vb, m, sacc);
-#else
-            m = fmaxf(m, va[0] + vb[31]);
-#endif
-            mm[r] = m;
-            ss[r] = sacc;
+          for (int i = 0; i < NC; i += 2) {
+            const float2 t = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(q[i], q[i + 1]));
+            v[i] = t.x; v[i + 1] = t.y;
           }
+          if (r == 0) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) q[i] = v[i];
+          }
+          float m = mm[r], sacc = ss[r];
+#ifndef GMM_NO_LSE
+          lse_stage<NC>(v, m, sacc);
+#else
+          m = fmaxf(m, v[0] + v[NC - 1]);
+#endif
+          mm[r] = m;
+          ss[r] = sacc;
+        }
+      } else {
+        float v[NC];
+        fetch(v);
+        if constexpr (kStore) {
+          float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + stage * FB_STAGE_N + half * NC);
+          const float ln2 = 0.6931471805599453f;
+#pragma unroll
+          for (int i = 0; i < NC; i += 4) dst[i >> 2] = make_float4(v[i] * ln2, v[i + 1] * ln2, v[i + 2] * ln2, v[i + 3] * ln2);
         } else {
-          float va[32], vb[32];
-          fetch(va, vb);
-          if constexpr (kStore) {
-            float4 *dst = reinterpret_cast<float4 *>(g.ll_out + (size_t)row * g.C + stage * FB_STAGE_N);
-            const float ln2 = 0.6931471805599453f;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) dst[i >> 2] = make_float4(va[i] * ln2, va[i + 1] * ln2, va[i + 2] * ln2, va[i + 3] * ln2);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) dst[8 + (i >> 2)] = make_float4(vb[i] * ln2, vb[i + 1] * ln2, vb[i + 2] * ln2, vb[i + 3] * ln2);
-          } else {
-            float m = mm[0], sacc = ss[0];
+          float m = mm[0], sacc = ss[0];
 #ifndef GMM_NO_LSE
-            lse_stage(va, vb, m, sacc);
+          lse_stage<NC>(v, m, sacc);
 #else
-            m = fmaxf(m, va[0] + vb[31]);
+          m = fmaxf(m, v[0] + v[NC - 1]);
 #endif
-            mm[0] = m;
-            ss[0] = sacc;
-          }
+          mm[0] = m;
+          ss[0] = sacc;
         }
       }
     }
     if (run_item >= 0) flush();
 #ifdef GMM_STATS
-    if (lane == 0 && (warp == 2 || warp == 6)) { g_gmm_stats[blockIdx.x * 16 + 10 + (warp == 6 ? 2 : 0)] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 11 + (warp == 6 ? 2 : 0)] = st_epi_full; }
+    if (lane == 0 && (warp == 3 || warp == 7)) { g_gmm_stats[blockIdx.x * 16 + 10 + (warp == 7 ? 2 : 0)] = clock64() - st_t0; g_gmm_stats[blockIdx.x * 16 + 11 + (warp == 7 ? 2 : 0)] = st_epi_full; }
 #endif
   }
   tc_fence_before();
@@ -622,6 +656,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 __global__ void __launch_bounds__(128)
 gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, float *__restrict__ frame_ll, int nst,
                  int rows_cap, const int *__restrict__ done_flag, int umma_grid, int models_per_unit) {
+  FB_GRID_DEP_SYNC();
   if (done_flag && *done_flag) return;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const int model = blockIdx.y;
@@ -629,7 +664,7 @@ gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, 
   if (row >= M) return;
   // The partials of this row are the segments gmm_umma_kernel cut its stage sequence into: recompute the CTA boundaries
   // floor(total * b / grid) that fall inside this (super-tile[, model]) item.
-  float2 p[64];                                  // C <= 4096: at most 64 stages, hence at most 64 segments
+  float2 p[64 * FB_GMM_EPI_HALVES];              // C <= 4096: at most 64 stages, hence at most 64 segments x column ranges
   int n = 0;
   {
     const int n_super = (M + 2 * FB_TILE_M - 1) / (2 * FB_TILE_M);
@@ -641,7 +676,9 @@ gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, 
       const long long b = ((st + 1) * umma_grid - 1) / total;                 // the CTA whose range contains stage st
       long long end = total * (b + 1) / umma_grid;
       if (end > g0 + nst) end = g0 + nst;
-      p[n++] = part[((size_t)model * nst + (int)(st - g0)) * rows_cap + row];
+#pragma unroll
+      for (int h = 0; h < FB_GMM_EPI_HALVES; ++h)
+        p[n++] = part[(((size_t)model * nst + (int)(st - g0)) * FB_GMM_EPI_HALVES + h) * rows_cap + row];
       st = end;
     }
   }
@@ -656,6 +693,7 @@ gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, 
 __global__ void __launch_bounds__(128)
 gmm_reduce_kernel(const float *__restrict__ frame_ll, const int *__restrict__ row_off, double *__restrict__ avg_ll,
                   int n_models, int rows_cap, const int *__restrict__ done_flag) {
+  FB_GRID_DEP_SYNC();
   if (done_flag && *done_flag) return;
   __shared__ double s_red[4];
   const int b = blockIdx.x, model = blockIdx.y;
@@ -775,9 +813,11 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
     // How many of the three fp16 products the difference sub-stages need.  The rounding error of a one-term product
     // x_hi . dw_hi is ~2^-12 |x| |dw| per dimension; with |x| ~ 1 after the power-of-two scaling, the per-frame error of
     // component c is ~2^-12 ||dw_c||.  E = 2^-12 sqrt(sum_c weight_c ||dw_c||^2), maximised over the slots, predicts it
-    // (scripts/gmm_precision_study.py: E = 6e-4 <-> frame error 7e-4 rms, utterance score deviation 1.1e-4 with one term,
-    // 4e-5 with two).  The automatic choice keeps the predicted score deviation below the 1e-4 resolution of the
-    // reference's 7-significant-digit text scores.
+    // (measured on the B200, tests/test_gpu_gmm.py / test_gpu_fullsize.py: E = 6.0e-4 (2048-mixture bench models) -> utterance
+    // score deviation from the three-term result 1.1e-4 with one term, 3.8e-5 with two; E = 1.2e-3 (256-mixture test models)
+    // -> 7.2e-4 and 1.2e-4).  The automatic choice keeps the deviation near the 1e-4 resolution of the reference's own
+    // 7-significant-digit text scores: two terms for MAP-adapted speaker models, one only for very small offsets, three
+    // when the slots are unrelated models.
     double E = 0.0;
     for (int m = 1; m < n_models; ++m) {
       double acc = 0.0, wsum = 0.0;
@@ -792,7 +832,7 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
     }
     ctx->delta_err_est = E;
     int terms = ctx->delta_terms_req;
-    if (terms == 0) terms = (E <= 8e-4) ? 1 : ((E <= 2.5e-3) ? 2 : 3);
+    if (terms == 0) terms = (E <= 2.5e-4) ? 1 : ((E <= 1.5e-3) ? 2 : 3);
     ctx->delta_terms = terms;
     // [stage][q = 0: x^2 part | q = 1: x part + gconst of slot 0 | q = 1+m: (slot m - slot 0) x part + gconst difference]
     // q < 2: [hi 10 slabs | lo 10 slabs][64 cols][8]; q >= 2: the same, or the hi half alone when terms == 1
@@ -871,14 +911,14 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     if (max_units < grid) grid = (int)max_units;
     umma_grid = grid;
     a.ll_out = nullptr;
-    if (ctx->gmm_shared) gmm_umma_kernel<false, true><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
-    else gmm_umma_kernel<false, false><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
+    if (ctx->gmm_shared) FB_CUDA(fb_launch(gmm_umma_kernel<false, true>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
+    else FB_CUDA(fb_launch(gmm_umma_kernel<false, false>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
   }
   fb_prof_mark(ctx, 4);
-  gmm_frame_kernel<<<dim3(fb_div_up(ctx->total_frames, 128), ctx->n_models), 128, 0, ctx->stream>>>(
-      ctx->part.p, ctx->misc.p, ctx->frame_ll.p, nst, ctx->rows_cap, done_flag, umma_grid, ctx->gmm_shared ? 1 : ctx->n_models);
-  gmm_reduce_kernel<<<dim3(ctx->B, ctx->n_models), 128, 0, ctx->stream>>>(ctx->frame_ll.p, ctx->row_off.p, ctx->avg_ll.p,
-                                                                         ctx->n_models, ctx->rows_cap, done_flag);
+  FB_CUDA(fb_launch(gmm_frame_kernel, dim3(fb_div_up(ctx->total_frames, 128), ctx->n_models), dim3(128), 0, ctx->stream,
+                    ctx->part.p, ctx->misc.p, ctx->frame_ll.p, nst, ctx->rows_cap, done_flag, umma_grid, ctx->gmm_shared ? 1 : ctx->n_models));
+  FB_CUDA(fb_launch(gmm_reduce_kernel, dim3(ctx->B, ctx->n_models), dim3(128), 0, ctx->stream, ctx->frame_ll.p, ctx->row_off.p,
+                    ctx->avg_ll.p, ctx->n_models, ctx->rows_cap, done_flag));
   fb_prof_mark(ctx, 5);
   ctx->launches += 3;
   FB_CUDA(cudaGetLastError());
@@ -905,7 +945,7 @@ int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag) {
   int grid = ctx->num_sms;
   if (max_units < grid) grid = (int)max_units;
   FB_CHECK_ARG(!ctx->gmm_shared, "Gaussian selection needs the general W image");
-  gmm_umma_kernel<true, false><<<grid, GMM_THREADS, kSmemLaunch, ctx->stream>>>(a);
+  FB_CUDA(fb_launch(gmm_umma_kernel<true, false>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
   fb_prof_mark(ctx, 4);
   ctx->launches += 1;
   FB_CUDA(cudaGetLastError());

@@ -60,6 +60,7 @@ __device__ __forceinline__ int16_t quantise(double v) {
 // grid (ceil(N/4/256), pair chunks), block 256; each thread owns 4 consecutive samples.
 __global__ void __launch_bounds__(256)
 perturb_kernel(FbNesDev st, int16_t *__restrict__ wave, int64_t stride, int philox) {
+  FB_GRID_DEP_SYNC();
   if (st.flags[0]) return;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n0 = g * 4;
@@ -189,7 +190,18 @@ __device__ void bookkeeping(const FbNesDev &st) {
   row[2] = final_loss;
   for (int k = 0; k < st.K; ++k) row[4 + k] = st.red[st.N + S + 1 + k];
   double lr = st.state_f64[0];
-  if (st.auto_stop && adver_loss < 0.0) {
+  if (st.est_mode) {
+    double sc = -INFINITY;
+    for (int k = 0; k < st.K; ++k) sc = fmax(sc, st.red[st.N + S + 1 + k]);     // np.max(score) for OSI, the score for SV
+    const int code = (sc >= st.accept_threshold) ? 2 : ((sc >= st.threshold[0]) ? 1 : 0);
+    if (code) {
+      row[3] = lr;
+      st.flags[0] = code;          // FAKEBOB.py:97-106: return / break before get_grad -- no update, the draw is not consumed
+      st.flags[2] = it;
+      st.flags[1] = it + 1;
+      return;
+    }
+  } else if (st.auto_stop && adver_loss < 0.0) {
     row[3] = lr;
     st.flags[0] = 1;             // early stop: no update (FAKEBOB.py:181-191)
     st.flags[2] = it;
@@ -220,6 +232,7 @@ __device__ void bookkeeping(const FbNesDev &st) {
 
 __global__ void __launch_bounds__(256)
 nes_loss_kernel(FbNesDev st, const double *__restrict__ avg_ll, int n_models, int do_book) {
+  FB_GRID_DEP_SYNC();
   if (st.flags[0]) return;
   const int bl = st.B_local;
   const int bclean = st.has_clean ? 1 : 0;
@@ -250,12 +263,14 @@ nes_loss_kernel(FbNesDev st, const double *__restrict__ avg_ll, int n_models, in
 }
 
 __global__ void nes_book_kernel(FbNesDev st) {
+  FB_GRID_DEP_SYNC();
   if (st.flags[0]) return;
   if (threadIdx.x == 0 && blockIdx.x == 0) bookkeeping(st);
 }
 
 // Zero the parts of the reduction buffer other ranks own (multi-GPU only).
 __global__ void nes_zero_red_kernel(FbNesDev st) {
+  FB_GRID_DEP_SYNC();
   if (st.flags[0]) return;
   const int n = st.S + 1 + st.K;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st.red[st.N + i] = 0.0;
@@ -277,6 +292,7 @@ struct ColGetter {
 
 __global__ void __launch_bounds__(128)
 nes_update_kernel(FbNesDev st, int mode, int use_state_lr, double lr_arg) {
+  FB_GRID_DEP_SYNC();
   if (st.flags[0]) return;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double dist = 0.0;
@@ -321,32 +337,40 @@ nes_update_kernel(FbNesDev st, int mode, int use_state_lr, double lr_arg) {
     atomicMax(&st.dist_bits[st.flags[1]], (unsigned long long)__double_as_longlong(dist));
 }
 
-// Single-GPU gradient + update with 8 lanes per sample: numpy's pairwise block (8 <= S <= 128) keeps 8 interleaved
-// accumulators r_c = a[c] + a[c+8] + ..., so lane c owns chain c (same additions, same order), the chains are combined as
-// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) with xor-shuffles (IEEE addition is commutative, so both partners get identical
-// bits) and the tail elements are added last -- bit-identical to np.mean(loss * noise, axis=1) with 8x the parallelism.
+// Single-GPU gradient + update, one thread per sample: numpy's pairwise block (8 <= S <= 128) keeps 8 interleaved
+// accumulators r_c = a[c] + a[c+8] + ..., combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), tail elements added last -- the
+// same additions in the same order, so the result is bit-identical to np.mean(loss * noise, axis=1).  Lane = sample: every
+// noise load of a warp is one contiguous 128-byte (float32) or 256-byte (float64) line, eight independent loads and
+// add chains in flight per thread; the losses sit in shared memory.
 // mode 0: estimate + update, mode 3: estimate only (get_grad).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 nes_update8_kernel(FbNesDev st, int mode) {
+  FB_GRID_DEP_SYNC();
   if (st.flags[0]) return;
-  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n = gt >> 3;
-  const int c = (int)(gt & 7);
+  __shared__ double s_loss[129];
+  const int S = st.S, S2 = st.pairs_total;
+  for (int i = threadIdx.x; i <= S; i += blockDim.x) s_loss[i] = st.red[st.N + i];
+  __syncthreads();
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = n < st.N;
   const int64_t nn = valid ? n : st.N - 1;
-  const double *loss = st.red + st.N;
-  const int S = st.S, S2 = st.pairs_total;
-  ColGetter get{st.noise, st.noise32, loss, st.N, nn, S2};
+  ColGetter get{st.noise, st.noise32, s_loss, st.N, nn, S2};
   const int full = S - (S % 8);
-  double r = get(c);
-  for (int i = 8 + c; i < full; i += 8) r = __dadd_rn(r, get(i));
-  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
-  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
-  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-  for (int i = full; i < S; ++i) r = __dadd_rn(r, get(i));
+  double r[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) r[c] = get(c);
+  for (int i = 8; i < full; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = get(i + c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) r[c] = __dadd_rn(r[c], v[c]);
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (int i = full; i < S; ++i) res = __dadd_rn(res, get(i));
   double dist = 0.0;
-  if (valid && c == 0) {
-    const double g = __ddiv_rn(__ddiv_rn(r, (double)S), st.sigma);
+  if (valid) {
+    const double g = __ddiv_rn(__ddiv_rn(res, (double)S), st.sigma);
     if (mode == 3) {
       st.gest[n] = g;
     } else {
@@ -542,7 +566,7 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
   int rc;
   dim3 gp(fb_div_up(fb_div_up(s->N, 4), 256), s->pairs_local > 0 ? (s->pairs_local < 8 ? s->pairs_local : 8) : 1);
   fb_prof_mark(ctx, -1);
-  perturb_kernel<<<gp, 256, 0, ctx->stream>>>(d, ctx->wave.p, s->N, philox);
+  FB_CUDA(fb_launch(perturb_kernel, gp, dim3(256), 0, ctx->stream, d, ctx->wave.p, s->N, philox));
   fb_prof_mark(ctx, 0);
   ctx->launches += 1;
   if ((rc = fb_run_frontend_flag(ctx, d.flags))) return rc;
@@ -559,24 +583,24 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
   }
   const int multi = s->world > 1;
   if (multi) {
-    nes_zero_red_kernel<<<1, 256, 0, ctx->stream>>>(d);
+    FB_CUDA(fb_launch(nes_zero_red_kernel, dim3(1), dim3(256), 0, ctx->stream, d));
     ctx->launches += 1;
   }
-  nes_loss_kernel<<<1, 256, 0, ctx->stream>>>(d, ll_dev, ll_stride, mode_get_grad ? 2 : (multi ? 0 : 1));
+  FB_CUDA(fb_launch(nes_loss_kernel, dim3(1), dim3(256), 0, ctx->stream, d, ll_dev, ll_stride, mode_get_grad ? 2 : (multi ? 0 : 1)));
   fb_prof_mark(ctx, 6);
   ctx->launches += 1;
   const int nb = fb_div_up(s->N, 128);
   if (!multi) {
     if (d.S >= 8 && d.S <= 128)
-      nes_update8_kernel<<<fb_div_up(s->N * 8, 256), 256, 0, ctx->stream>>>(d, mode_get_grad ? 3 : 0);
+      FB_CUDA(fb_launch(nes_update8_kernel, dim3(fb_div_up(s->N, 128)), dim3(128), 0, ctx->stream, d, mode_get_grad ? 3 : 0));
     else
-      nes_update_kernel<<<nb, 128, 0, ctx->stream>>>(d, mode_get_grad ? 3 : 0, 1, 0.0);
+      FB_CUDA(fb_launch(nes_update_kernel, dim3(nb), dim3(128), 0, ctx->stream, d, mode_get_grad ? 3 : 0, 1, 0.0));
     ctx->launches += 1;
   } else {
-    nes_update_kernel<<<nb, 128, 0, ctx->stream>>>(d, 1, 1, 0.0);
+    FB_CUDA(fb_launch(nes_update_kernel, dim3(nb), dim3(128), 0, ctx->stream, d, 1, 1, 0.0));
     if ((rc = fb_comm_allreduce_f64(ctx, d.red, s->red_count))) return rc;
-    nes_book_kernel<<<1, 32, 0, ctx->stream>>>(d);
-    nes_update_kernel<<<nb, 128, 0, ctx->stream>>>(d, 2, 1, 0.0);
+    FB_CUDA(fb_launch(nes_book_kernel, dim3(1), dim3(32), 0, ctx->stream, d));
+    FB_CUDA(fb_launch(nes_update_kernel, dim3(nb), dim3(128), 0, ctx->stream, d, 2, 1, 0.0));
     ctx->launches += 3;
   }
   fb_prof_mark(ctx, 7);
@@ -671,6 +695,33 @@ extern "C" int fb_nes_set_threshold(fb_ctx *ctx, double threshold) {
   ctx->nes->p.threshold = threshold;
   FB_CUDA(cudaMemcpyAsync(ctx->nes->dev.threshold, &ctx->nes->p.threshold, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_nes_estimate_begin(fb_ctx *ctx, double accept_threshold) {
+  FB_CHECK_ARG(ctx && ctx->nes, "fb_nes_init has not been called");
+  FbNes *s = ctx->nes;
+  FB_CHECK_ARG(s->p.task != FB_TASK_CSI && !s->p.targeted, "estimate mode is the untargeted OSI / SV search (FAKEBOB.py:41-43,73-74)");
+  FB_CHECK_ARG(s->world == 1, "estimate mode is single-GPU only");
+  s->dev.est_mode = 1;
+  s->dev.accept_threshold = accept_threshold;        // the captured graph is keyed on the device arguments: re-captured on next run
+  return FB_OK;
+}
+
+extern "C" int fb_nes_continue(fb_ctx *ctx, double threshold) {
+  FB_CHECK_ARG(ctx && ctx->nes, "fb_nes_init has not been called");
+  FbNes *s = ctx->nes;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  s->p.threshold = threshold;
+  const double lr0 = s->p.max_lr;
+  FB_CUDA(cudaMemcpyAsync(s->dev.threshold, &s->p.threshold, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FB_CUDA(cudaMemcpyAsync(s->dev.state_f64, &lr0, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));   // lr = max_lr (FAKEBOB.py:82)
+  FB_CUDA(cudaMemsetAsync(s->dev.flags, 0, sizeof(int), ctx->stream));                                       // not stopped
+  FB_CUDA(cudaMemsetAsync(s->dev.flags + 3, 0, sizeof(int), ctx->stream));                                   // last_ls = []
+  int done = 0;                                                      // iterations enqueued after the stop were no-ops
+  FB_CUDA(cudaMemcpyAsync(&done, s->dev.flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  s->enqueued = done;
   return FB_OK;
 }
 

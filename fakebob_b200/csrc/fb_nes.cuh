@@ -20,6 +20,11 @@ struct FbNesDev {
   int task, targeted, label, plateau_length, auto_stop, znorm;
   double kappa, sigma, epsilon, momentum, one_minus_momentum, min_lr, plateau_drop;
   unsigned long long seed;
+  // estimate_threshold mode (FAKEBOB.py:82-113): the clean column of every batch is the make_decisions() score of the current
+  // adversarial audio, so the stop tests run on the device: accepted by the system (score >= accept_threshold, flags[0] = 2)
+  // or candidate threshold reached (score >= theta, flags[0] = 1); neither consumes the iteration's noise draw.
+  int est_mode;
+  double accept_threshold;
 };
 
 // One per context, created by the first fb_nes_init and reused by every later session: the device buffers only grow

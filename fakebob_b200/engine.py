@@ -216,9 +216,16 @@ class GmmEngine:
         _lib.check(self.lib.fb_nes_run(self.h, n_iters, _ptr(noise) if noise is not None else None))
 
     def nes_status(self):
+        """-> (iterations done, stop code: 0 running, 1 early stop / candidate threshold reached, 2 accepted (estimate mode))."""
         it, st = C.c_int(0), C.c_int(0)
         _lib.check(self.lib.fb_nes_status(self.h, C.byref(it), C.byref(st)))
-        return it.value, bool(st.value)
+        return it.value, st.value
+
+    def nes_estimate_begin(self, accept_threshold):
+        _lib.check(self.lib.fb_nes_estimate_begin(self.h, float(accept_threshold)))
+
+    def nes_continue(self, threshold):
+        _lib.check(self.lib.fb_nes_continue(self.h, float(threshold)))
 
     def nes_log(self, max_rows):
         rows = np.zeros((max_rows, 4 + self._nes_K), dtype=np.float64)

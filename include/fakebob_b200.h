@@ -166,12 +166,22 @@ int fb_nes_set_threshold(fb_ctx *ctx, double threshold);
 /* Enqueue up to n_iters iterations (stops early on device when adver_loss < 0).  rng = HOST: noise_host
  * is n_iters x (S/2) x n_samples float64 (pair-major), else NULL.  Asynchronous. */
 int fb_nes_run(fb_ctx *ctx, int n_iters, const double *noise_host);
-/* Blocks until enqueued work finished; returns iterations executed so far and whether early stop hit. */
+/* Blocks until enqueued work finished; returns iterations executed so far and the stop code (0 = running, 1 = early stop /
+ * candidate threshold reached, 2 = accepted by the system in estimate mode). */
 int fb_nes_status(fb_ctx *ctx, int *iters_done, int *stopped);
 /* Log rows [iter] = {distance, adver_loss, final_loss, lr, score_0..score_{K-1}} (float64, 4+K per row). */
 int fb_nes_read_log(fb_ctx *ctx, double *rows_host, int max_rows);
 int fb_nes_read_adver(fb_ctx *ctx, double *adver_host, int64_t n_samples);
 int fb_nes_read_grad(fb_ctx *ctx, double *grad_host, int64_t n_samples);
+/* FakeBob.estimate_threshold on the device (FAKEBOB.py:76-137).  The reference scores the current adversarial audio with
+ * make_decisions() and then, separately, the S+1 batch of get_grad(); column 0 of that batch IS the current audio, so one
+ * batch per inner iteration serves both.  After fb_nes_init (untargeted OSI / SV, max_iter = an upper bound on the total
+ * number of inner iterations): fb_nes_estimate_begin(accept_threshold = the system's own threshold, model.threshold),
+ * then per outer iteration fb_nes_continue(theta) -- sets theta, lr = max_lr, empties the plateau window, clears the stop
+ * flag -- and fb_nes_run / fb_nes_status until `stopped` is 1 (score >= theta: next outer iteration) or 2 (accepted: done).
+ * The stopping iteration applies no update and does not consume its noise draw, like the reference's break / return. */
+int fb_nes_estimate_begin(fb_ctx *ctx, double accept_threshold);
+int fb_nes_continue(fb_ctx *ctx, double threshold);
 /* One gradient estimate without the update: FakeBob.get_grad (FAKEBOB.py:223-246). */
 int fb_nes_get_grad(fb_ctx *ctx, const double *noise_host, double *final_loss, double *adver_loss,
                     double *score0_host, double *grad_host);

@@ -1,0 +1,8 @@
+#!/bin/bash
+TAG=${1:-s4}
+mkdir -p gpurun_out
+sed -i 's/for t in 1 3; do/for t in 1 2; do/' scripts/gmm_ab.sh
+bash scripts/gmm_ab.sh ${TAG}
+( timeout 900 python -m pytest tests -m gpu -q -rA 2>&1 ) > gpurun_out/${TAG}_tests.log
+( timeout 300 python bench.py --steps 50 --warmup 10 --no-extra 2>&1 | tail -2 ) > gpurun_out/${TAG}_bench.log
+echo done

@@ -105,7 +105,6 @@ def test_iv_attack_bit_exact_given_same_scores(small_iv_tree, iv_osi, task):
     fb = FakeBob(task, "untargeted", model, rng="numpy", verbose=False, **hp)
     adv_g, flag_g = fb.attack(audio.copy(), None, **kw)
     np.random.seed(3)
-    _ = np.random.randint(0, 2 ** 62)
     ob = OracleFakeBob(task, "untargeted", model, **hp)
     adv_o, flag_o = ob.attack(audio.copy(), None, **kw)
     assert flag_g == flag_o and fb.iters_done == len(ob.log)

@@ -182,6 +182,32 @@ def test_device_error_is_reported_once_with_its_own_code(scorers):
     assert np.isfinite(ok)
 
 
+@pytest.mark.parametrize("task", ["OSI", "SV"])
+def test_estimate_threshold_on_device_matches_oracle_search(scorers, task, capsys):
+    """rng='philox': the whole inner loop of FAKEBOB.py:76-137 runs on the device (the clean column of each NES batch is the
+    make_decisions() score); same Philox stream and scorer as the restated reference -> same number of iterations, same
+    returned score up to the batch-composition tolerance of the scorer."""
+    from fakebob_b200.FAKEBOB import FakeBob
+    from oracle.nes import OracleFakeBob, PhiloxNoise
+    model = scorers[task]
+    audio = make_audio(41, 1, n=16000)
+    s0 = model.score(audio)
+    model.threshold = float(np.max(s0)) + 0.02                      # rejected now, reachable within the epsilon ball
+    try:
+        fb = FakeBob(task, "targeted", model, samples_per_draw=8, seed=4242, verbose=True, max_lr=0.001, iters_per_launch=4)
+        r1 = fb.estimate_threshold(audio)
+        out = capsys.readouterr().out
+        ob = OracleFakeBob(task, "targeted", model, samples_per_draw=8, max_lr=0.001, noise_fn=PhiloxNoise(4242))
+        r2 = ob.estimate_threshold(audio)
+    finally:
+        model.threshold = 0.0
+    assert fb.attack_type == "targeted"
+    assert "----- iter_outer:0" in out and "return at iter_outer" in out and "cost %d iters" % r1[1] in out
+    assert r1[1] == r2[1] and r1[1] >= 1                           # inner iterations with an update
+    assert abs(float(r1[0]) - float(r2[0])) < 5e-4
+    assert abs(fb.threshold - ob.threshold) < 5e-4 and fb.draws == ob.draws
+
+
 def test_requires_device_backed_model():
     from fakebob_b200.FAKEBOB import FakeBob
 

@@ -74,6 +74,33 @@ def test_feature_config_from_pre_models(tmp_path):
     assert load_feature_config(str(tmp_path / "missing")).num_mel_bins == 30
 
 
+def test_feature_config_rejects_options_the_kernels_do_not_implement(tmp_path):
+    """mfcc.conf keys that change the features must not be dropped silently (the reference hands the file to Kaldi,
+    gmm_ubm_kaldiHelper.py:138): every Kaldi MFCC option is parsed, unsupported values raise, unknown keys warn."""
+    import warnings
+    for line, ok in (("--use-energy=false", False), ("--raw-energy=false", False), ("--energy-floor=1.0", False),
+                     ("--window-type=hamming", False), ("--remove-dc-offset=false", False), ("--dither=1.0", False),
+                     ("--htk-compat=true", False), ("--use-energy=true", True), ("--dither=0", True), ("--window-type=povey", True)):
+        d = tmp_path / line.strip("-").replace("=", "_")
+        synth.write_conf(str(d))
+        with open(str(d / "conf" / "mfcc.conf"), "a") as f:
+            f.write(line + "\n")
+        cfg = load_feature_config(str(d))
+        if ok:
+            cfg.check_supported()
+        else:
+            with pytest.raises(ValueError):
+                cfg.check_supported()
+    d = tmp_path / "unknown"
+    synth.write_conf(str(d))
+    with open(str(d / "conf" / "mfcc.conf"), "a") as f:
+        f.write("--vtln-low=100\n")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        load_feature_config(str(d)).check_supported()
+    assert any("vtln-low" in str(x.message) for x in w)
+
+
 def test_audio_input_conventions():
     a = np.linspace(-0.5, 0.5, 100)
     for arr in (a, a[:, None], a[None, :]):
