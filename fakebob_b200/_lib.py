@@ -81,6 +81,8 @@ _SIGS = {
     "fb_comm_unique_id": (C.c_int, [_P]),
     "fb_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "fb_comm_destroy": (C.c_int, [_P]),
+    "fb_comm_p2p_export": (C.c_int, [_P, C.c_int64, _P]),
+    "fb_comm_p2p_import": (C.c_int, [_P, _P]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -156,6 +156,10 @@ int fb_map_device_error(fb_ctx *ctx, int code) {
     fb_set_error("an utterance is too long for the i-vector statistics kernel");
     return FB_ERR_TOO_LONG;
   }
+  if (code == 4) {
+    fb_set_error("multi-GPU exchange timed out waiting for a peer rank's partial gradient");
+    return FB_ERR_NCCL;
+  }
   if (code == 3) {
     fb_set_error("i-vector posterior precision matrix (quad + I) is not positive definite");
     return FB_ERR_NOT_SPD;

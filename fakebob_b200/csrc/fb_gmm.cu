@@ -37,8 +37,9 @@
 // the cut points to merge them.
 // Shared-variance mode (all slots share their inverse variances, as MAP mean-only adaptation produces): per (rows, 64-column
 // stage) the ring carries  q = 0: x^2 . (-0.5/var),  q = 1: x . w_0 + g_0  (slot 0, normally the UBM),
-// q = 1 + m: x . (w_m - w_0) + (g_m - g_0)  for every other slot, and the epilogue forms  ll_0 = Q + T_0,  ll_m = ll_0 + D_m.
-// Q and T_0 always use the three-term split; the difference sub-stages use `delta_terms` of the three products
+// q = 1 + m: x . (w_m - w_0) + (g_m - g_0)  for every other slot.  The issuers accumulate q = 0 and q = 1 into ONE accumulator
+// (ll_0, 30 MMAs); each difference sub-stage D_m gets its own (5 MMAs per product term) and the epilogue forms ll_m = ll_0 + D_m.
+// ll_0 always uses the three-term split; the difference sub-stages use `delta_terms` of the three products
 // (1: hi.hi, 2: hi.hi + hi.lo, 3: all) -- the differences are small, so their fp16 rounding error is small in absolute
 // terms (scripts/gmm_precision_study.py; fb_set_gmm_delta_terms in the header).
 // Tried and rejected (same-clock A/B, cycles per CTA): 16 epilogue warps of 32 columns (+5 %); four accumulators (two per
@@ -81,13 +82,8 @@ static_assert(kSmemLaunch <= 232448, "exceeds the 227 KB per-CTA shared memory l
 // TMEM columns (all 512 used): three 64-column accumulators [0,192) used as a ring over (tile, sub-step) jobs, so the
 // MMA <-> epilogue hand-shake latency is hidden behind two jobs; A operand: tile t at 192 + 160 t: hi 80 columns, lo 80 columns
 static constexpr uint32_t kTmemAcc = 0;
-#ifdef GMM_ACC5_HACK      // TIMING EXPERIMENT ONLY (wrong numerics): five accumulators, the lo halves of A alias other columns
-static constexpr uint32_t kNumAcc = 5;
-static constexpr uint32_t kTmemA = 320;
-#else
 static constexpr uint32_t kNumAcc = 3;
 static constexpr uint32_t kTmemA = 192;
-#endif
 static constexpr uint32_t kTmemAHalfCols = FB_A_HI_SLABS * 4;                  // 80
 static constexpr uint32_t kTmemATileCols = 2 * kTmemAHalfCols;                 // 160
 static constexpr uint32_t kTmemX2Cols = FB_SLAB_X2 * 4;                        // 40: column offset of the x^2 half
@@ -257,16 +253,18 @@ __device__ __forceinline__ void lse_stage(const float *v, float &m, float &s) {
 #pragma unroll
   for (int k = 0; k < NG; ++k) {
     if (alive[k]) {
+      // Kaldi's cutoff is applied per group: a group all of whose terms lie below max - 23 is skipped; inside a surviving
+      // group every term is added (those below the cutoff contribute < 2^-23 of the largest term each), which keeps the
+      // arithmetic packed: 4 FADD2, 8 EX2, 3 FADD2 + 1 FADD per group of 8
       const float *q = v + GS * k;
-      float s0 = 0.f, s1 = 0.f;
+      const float2 nm = make_float2(-m, -m);
+      float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < GS; i += 2) {
-        const float t0 = q[i] - m, t1 = q[i + 1] - m;
-        const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
-        if (t0 >= -23.0f) s0 += e0;
-        if (t1 >= -23.0f) s1 += e1;
+        const float2 t = __fadd2_rn(make_float2(q[i], q[i + 1]), nm);
+        acc2 = __fadd2_rn(acc2, make_float2(ex2_approx(t.x), ex2_approx(t.y)));
       }
-      s += s0 + s1;
+      s += acc2.x + acc2.y;
     }
   }
 }
@@ -338,7 +336,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
   const long long n_units = (long long)n_super * models_per_unit * nst;
   const int u0 = (int)(n_units * blockIdx.x / gridDim.x);
   const int u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
-  const int n_sub = kShared ? g.n_models + 1 : 1;                              // sub-stages (jobs per tile) per 64-column stage
+  const int n_sub = kShared ? g.n_models : 1;                                  // jobs per tile per 64-column stage
   const SharedLayout SL = shared_layout(g.n_models, g.delta_terms);
 
   tc_fence_before();
@@ -446,11 +444,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           if (elect_one()) {
             if ((e >> 1) == tile) {
               const uint64_t src = desc_a + (uint64_t)(((base + slot * kSlotBytes) & 0x3FFFFu) >> 4);
-#ifdef GMM_ACC5_HACK
-              const uint32_t dst = tmem_base + ((e & 1) ? 432u : kTmemA + tile * kTmemAHalfCols);
-#else
               const uint32_t dst = tmem_base + kTmemA + tile * kTmemATileCols + (e & 1) * kTmemAHalfCols;
-#endif
 #pragma unroll
               for (int kb = 0; kb < FB_A_HI_SLABS / 2; ++kb) tc_cp_128x256b(dst + kb * 8, src + (uint64_t)(kb * ((2 * kSlabA) >> 4)));
               tc_commit(bar_empty + 8 * slot);
@@ -467,48 +461,64 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
         for (int q = 0; q < n_sub; ++q) {
           const uint32_t slot = cnt % kNumSlots;
-          // position of sub-stage q inside its ring entry (shared mode: {0, 1}, then groups of difference sub-stages)
+          // shared mode: job 0 = slot 0 complete (x^2 and x sub-blocks of ring entry {0, 1}, one accumulator), job q >= 1 = the
+          // difference sub-stage of slot q, in groups of SL.group per ring entry
           bool first_in_slot = true, last_in_slot = true;
-          uint32_t sub_off = 0, half_bytes = kWHalfBytes, mask = 7u;
+          uint32_t sub_off = 0, mask = 7u;
           if constexpr (kShared) {
-            if (q < 2) {
-              first_in_slot = q == 0; last_in_slot = q == 1; sub_off = q ? kWShBytes : 0; half_bytes = kWShHalfBytes;
-            } else {
-              const uint32_t j = (uint32_t)(q - 2), r = j % SL.group;
+            if (q >= 1) {
+              const uint32_t j = (uint32_t)(q - 1), r = j % SL.group;
               first_in_slot = r == 0; last_in_slot = r == SL.group - 1 || q + 1 == n_sub;
-              sub_off = r * SL.dbytes; half_bytes = kWShHalfBytes; mask = SL.mask;
+              sub_off = r * SL.dbytes; mask = SL.mask;
             }
           }
           if (first_in_slot) STAT_WAIT(st_mma_full, bar_full + 8 * slot, (cnt / kNumSlots) & 1);
           const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes + sub_off) & 0x3FFFFu) >> 4);
-          const uint64_t w_lo = w_hi + (uint64_t)(half_bytes >> 4);
-          // shared mode: q = 0 is the x^2 sub-step, q >= 1 the x (+ gconst) sub-steps; all start from zero
-          const uint32_t a_off = (kShared && q == 0) ? kTmemX2Cols : 0;
           const uint32_t abuf = job % kNumAcc;
           // accumulator abuf was last used by job - 3, a job of the other tile: wait until that tile's epilogue has read it
           if (job >= kNumAcc) STAT_WAIT(st_mma_acc, bar_acc_empty + 8 * (2 * abuf + (tile ^ 1)), ((job - kNumAcc) / (2 * kNumAcc)) & 1);
           tc_fence_after();
           if (elect_one()) {
-#ifdef GMM_ACC5_HACK
-            const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemAHalfCols + a_off;
-            const uint32_t a_lo = tmem_base + 432u + a_off;
-#else
-            const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols + a_off;
+            const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols;
             const uint32_t a_lo = a_hi + kTmemAHalfCols;
-#endif
             const uint32_t d_tmem = tmem_base + kTmemAcc + abuf * FB_STAGE_N;
-            constexpr int nkb = kShared ? 5 : 10;
+            if constexpr (kShared) {
+              if (q == 0) {
+                // ll_0 = x^2 . (-0.5/var) + x . w_0 + g_0 in one accumulator: 3 terms x (5 + 5) k-blocks.  Ring entry:
+                // [x^2 block: hi 10 slabs | lo 10 slabs][x block: hi | lo]; A: x at column 0, x^2 at kTmemX2Cols.
+                const uint64_t q_hi = w_hi, q_lo = w_hi + (uint64_t)(kWShHalfBytes >> 4);
+                const uint64_t t_hi = w_hi + (uint64_t)(kWShBytes >> 4), t_lo = t_hi + (uint64_t)(kWShHalfBytes >> 4);
 #pragma unroll
-            for (int part = 0; part < GMM_PARTS; ++part) {
-              if (!((mask >> part) & 1u)) continue;
-#ifdef GMM_ACC5_HACK
-              if (part == 1) continue;                 // the aliased lo operand holds garbage: keep the values realistic
-#endif
-              const uint32_t a_base = (part == 1) ? a_lo : a_hi;
-              const uint64_t b_base = (part == 2) ? w_lo : w_hi;
+                for (int part = 0; part < GMM_PARTS; ++part) {
+                  const uint32_t a_base = (part == 1) ? a_lo : a_hi;
 #pragma unroll
-              for (int kb = 0; kb < nkb; ++kb) {
-                tc_mma_f16_ta(d_tmem, a_base + kb * 8, b_base + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
+                  for (int kb = 0; kb < 5; ++kb)
+                    tc_mma_f16_ta(d_tmem, a_base + kb * 8, ((part == 2) ? t_lo : t_hi) + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
+#pragma unroll
+                  for (int kb = 0; kb < 5; ++kb)
+                    tc_mma_f16_ta(d_tmem, a_base + kTmemX2Cols + kb * 8, ((part == 2) ? q_lo : q_hi) + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, 1u);
+                }
+              } else {
+                const uint64_t w_lo = w_hi + (uint64_t)(kWShHalfBytes >> 4);
+#pragma unroll
+                for (int part = 0; part < GMM_PARTS; ++part) {
+                  if (!((mask >> part) & 1u)) continue;
+                  const uint32_t a_base = (part == 1) ? a_lo : a_hi;
+                  const uint64_t b_base = (part == 2) ? w_lo : w_hi;
+#pragma unroll
+                  for (int kb = 0; kb < 5; ++kb)
+                    tc_mma_f16_ta(d_tmem, a_base + kb * 8, b_base + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
+                }
+              }
+            } else {
+              const uint64_t w_lo = w_hi + (uint64_t)(kWHalfBytes >> 4);
+#pragma unroll
+              for (int part = 0; part < GMM_PARTS; ++part) {
+                const uint32_t a_base = (part == 1) ? a_lo : a_hi;
+                const uint64_t b_base = (part == 2) ? w_lo : w_hi;
+#pragma unroll
+                for (int kb = 0; kb < 10; ++kb)
+                  tc_mma_f16_ta(d_tmem, a_base + kb * 8, b_base + (uint64_t)(kb * ((2 * kSlabW) >> 4)), kIdesc, (part | kb) ? 1u : 0u);
               }
             }
             tc_commit(bar_acc_full + 8 * (2 * abuf + tile));
@@ -583,20 +593,26 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         seg_start = stage; seg_row = row; seg_model = model;
       }
       if constexpr (kShared) {
-        float q[NC];                                    // Q (x^2 term), then ll_0 = Q + T_0: the base every other slot adds to
+        float q[NC];                                    // ll_0 of this (rows, column range): the base every other slot adds to
         fetch(q);
+        {
+          float m = mm[0], sacc = ss[0];
+#ifndef GMM_NO_LSE
+          lse_stage<NC>(q, m, sacc);
+#else
+          m = fmaxf(m, q[0] + q[NC - 1]);
+#endif
+          mm[0] = m;
+          ss[0] = sacc;
+        }
 #pragma unroll 1
-        for (int r = 0; r < g.n_models; ++r) {
+        for (int r = 1; r < g.n_models; ++r) {
           float v[NC];
           fetch(v);
 #pragma unroll
           for (int i = 0; i < NC; i += 2) {
             const float2 t = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(q[i], q[i + 1]));
             v[i] = t.x; v[i + 1] = t.y;
-          }
-          if (r == 0) {
-#pragma unroll
-            for (int i = 0; i < NC; ++i) q[i] = v[i];
           }
           float m = mm[r], sacc = ss[r];
 #ifndef GMM_NO_LSE

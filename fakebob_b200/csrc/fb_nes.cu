@@ -391,6 +391,129 @@ nes_update8_kernel(FbNesDev st, int mode) {
     atomicMax(&st.dist_bits[st.flags[1]], (unsigned long long)__double_as_longlong(dist));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU iteration over peer memory (FbNesDev::xown != NULL): partial -> publish -> gather + bookkeeping -> gather + update.
+// Writes are local, reads are remote (volatile, straight to the owner's L2 over NVLink); a flag per parity orders them.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_peer(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
+
+// partial gradient sum over this rank's pairs, one thread per sample (coalesced noise rows); -> own exchange buffer (or red)
+__global__ void __launch_bounds__(128)
+nes_partial_kernel(FbNesDev st) {
+  FB_GRID_DEP_SYNC();
+  if (st.flags[0]) return;
+  __shared__ double s_lp[128], s_lm[128];
+  const int P = st.pairs_local;
+  const double *loss = st.red + st.N;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int par = st.flags[1] & 1;
+  double *out = st.xown ? st.xown + (size_t)par * st.xstride : st.red;
+  double acc = 0.0;
+  for (int j0 = 0; j0 < P; j0 += 128) {
+    const int nj = min(128, P - j0);
+    __syncthreads();
+    if ((int)threadIdx.x < nj) {
+      s_lp[threadIdx.x] = loss[1 + st.pair0 + j0 + threadIdx.x];
+      s_lm[threadIdx.x] = loss[1 + st.pairs_total + st.pair0 + j0 + threadIdx.x];
+    }
+    __syncthreads();
+    if (n < st.N) {
+      for (int j = 0; j < nj; ++j) {
+        const double z = st.noise32 ? (double)st.noise32[(int64_t)(j0 + j) * st.N + n] : st.noise[(int64_t)(j0 + j) * st.N + n];
+        acc = __dadd_rn(acc, __dmul_rn(s_lp[j], z));
+        acc = __dadd_rn(acc, __dmul_rn(s_lm[j], -z));
+      }
+    }
+  }
+  if (n < st.N) out[n] = acc;
+}
+
+// copies this rank's losses / clean scores next to its partial and raises the flag of the iteration's parity
+__global__ void __launch_bounds__(256)
+nes_publish_kernel(FbNesDev st) {
+  FB_GRID_DEP_SYNC();
+  if (st.flags[0]) return;
+  const int it = st.flags[1];
+  const int par = it & 1;
+  double *own = st.xown + (size_t)par * st.xstride;
+  const int tail = st.S + 1 + st.K;
+  for (int i = threadIdx.x; i < tail; i += blockDim.x) own[st.N + i] = st.red[st.N + i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long v = (*st.xsess << 32) | (unsigned long long)(it + 1);
+    *reinterpret_cast<volatile unsigned long long *>(&st.xflag[par]) = v;
+    __threadfence_system();
+  }
+}
+
+// waits for every rank's flag, adds the loss / score tails in rank order into the local reduction buffer, bookkeeping
+__global__ void __launch_bounds__(256)
+nes_gather_book_kernel(FbNesDev st, int *__restrict__ err) {
+  FB_GRID_DEP_SYNC();
+  if (st.flags[0]) return;
+  __shared__ int s_bad;
+  const int it = st.flags[1];
+  const int par = it & 1;
+  const unsigned long long want = (*st.xsess << 32) | (unsigned long long)(it + 1);
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < st.world) {
+    const volatile unsigned long long *f = st.xpeer_flag[threadIdx.x] + par;
+    const long long t0 = clock64();
+    while (*f < want) {
+      if (clock64() - t0 > (6ll << 30)) { s_bad = 1; break; }       // ~3 s: a peer died; report instead of hanging the box
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (threadIdx.x == 0) { atomicExch(err, 4); st.flags[0] = 1; }
+    return;
+  }
+  const int tail = st.S + 1 + st.K;
+  for (int i = threadIdx.x; i < tail; i += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < st.world; ++r) acc = __dadd_rn(acc, ld_peer(st.xpeer[r] + (size_t)par * st.xstride + st.N + i));
+    st.red[st.N + i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) bookkeeping(st);
+}
+
+// gradient = sum of the W partials in rank order (identical on every rank), then the update; one thread per sample
+__global__ void __launch_bounds__(128)
+nes_gather_update_kernel(FbNesDev st) {
+  FB_GRID_DEP_SYNC();
+  if (st.flags[0]) return;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int par = (st.flags[1] - 1) & 1;                        // bookkeeping already advanced the iteration counter
+  double dist = 0.0;
+  if (n < st.N) {
+    double v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = (r < st.world) ? ld_peer(st.xpeer[r] + (size_t)par * st.xstride + n) : 0.0;
+    double sum = v[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+      if (r < st.world) sum = __dadd_rn(sum, v[r]);
+    const double g = __ddiv_rn(__ddiv_rn(sum, (double)st.S), st.sigma);
+    const double lr = st.state_f64[0];
+    const double G = __dadd_rn(__dmul_rn(st.momentum, st.grad[n]), __dmul_rn(st.one_minus_momentum, g));
+    st.grad[n] = G;
+    const double sg = (G > 0.0) ? 1.0 : ((G < 0.0) ? -1.0 : G);
+    double a = __dadd_rn(st.adver[n], -__dmul_rn(lr, sg));
+    a = fmin(fmax(a, st.lower[n]), st.upper[n]);
+    st.adver[n] = a;
+    dist = fabs(__dadd_rn(st.audio[n], -a));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dist = fmax(dist, __shfl_xor_sync(0xffffffffu, dist, o));
+  if ((threadIdx.x & 31) == 0 && dist > 0.0)
+    atomicMax(&st.dist_bits[st.flags[1]], (unsigned long long)__double_as_longlong(dist));
+}
+
 // adver <- clip(adver - lr * sign(momentum * grad + (1 - momentum) * gest))   (after get_grad)
 __global__ void __launch_bounds__(128) nes_apply_kernel(FbNesDev st, double lr) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,6 +660,8 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   d.kappa = p->adver_thresh; d.sigma = p->sigma; d.epsilon = p->epsilon; d.momentum = p->momentum;
   d.one_minus_momentum = 1.0 - p->momentum;
   d.min_lr = p->min_lr; d.plateau_drop = p->plateau_drop; d.seed = p->seed;
+  d.world = world; d.rank = rank;
+  if ((rc = fb_comm_p2p_attach(ctx, &d, red_n))) return rc;
   FB_CUDA(cudaMemcpyAsync(d.audio, audio_host, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (d.znorm) {
     FB_CUDA(cudaMemcpyAsync(d.zmean, p->z_norm_means, K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -597,11 +722,19 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
       FB_CUDA(fb_launch(nes_update_kernel, dim3(nb), dim3(128), 0, ctx->stream, d, mode_get_grad ? 3 : 0, 1, 0.0));
     ctx->launches += 1;
   } else {
-    FB_CUDA(fb_launch(nes_update_kernel, dim3(nb), dim3(128), 0, ctx->stream, d, 1, 1, 0.0));
-    if ((rc = fb_comm_allreduce_f64(ctx, d.red, s->red_count))) return rc;
-    FB_CUDA(fb_launch(nes_book_kernel, dim3(1), dim3(32), 0, ctx->stream, d));
-    FB_CUDA(fb_launch(nes_update_kernel, dim3(nb), dim3(128), 0, ctx->stream, d, 2, 1, 0.0));
-    ctx->launches += 3;
+    FB_CUDA(fb_launch(nes_partial_kernel, dim3(nb), dim3(128), 0, ctx->stream, d));
+    if (d.xown) {
+      // one-shot exchange over peer memory: no collective kernel, the W partials are added inside the update
+      FB_CUDA(fb_launch(nes_publish_kernel, dim3(1), dim3(256), 0, ctx->stream, d));
+      FB_CUDA(fb_launch(nes_gather_book_kernel, dim3(1), dim3(256), 0, ctx->stream, d, ctx->misc.p + 1));
+      FB_CUDA(fb_launch(nes_gather_update_kernel, dim3(nb), dim3(128), 0, ctx->stream, d));
+      ctx->launches += 4;
+    } else {
+      if ((rc = fb_comm_allreduce_f64(ctx, d.red, s->red_count))) return rc;
+      FB_CUDA(fb_launch(nes_book_kernel, dim3(1), dim3(32), 0, ctx->stream, d));
+      FB_CUDA(fb_launch(nes_update_kernel, dim3(nb), dim3(128), 0, ctx->stream, d, 2, 1, 0.0));
+      ctx->launches += 3;
+    }
   }
   fb_prof_mark(ctx, 7);
   FB_CUDA(cudaGetLastError());

@@ -25,6 +25,16 @@ struct FbNesDev {
   // or candidate threshold reached (score >= theta, flags[0] = 1); neither consumes the iteration's noise draw.
   int est_mode;
   double accept_threshold;
+  // multi-GPU one-shot exchange over peer memory (fb_comm.cu): every rank publishes [grad partial (N) | losses | clean
+  // scores] in its OWN buffer (two parities) and raises a flag; every rank then pulls the W partials over NVLink and adds
+  // them in rank order inside the update kernel -- no ring, no separate collective kernel.  NULL: ncclAllReduce instead.
+  double *xown;                    // [2][xstride]
+  unsigned long long *xflag;       // [2] own flags, value = (session << 32) | (iteration + 1)
+  const unsigned long long *xsess; // device word holding the session number (so the captured graph survives new sessions)
+  const double *xpeer[8];          // every rank's buffer (own included), mapped
+  const unsigned long long *xpeer_flag[8];
+  unsigned long long xstride;
+  int world, rank;
 };
 
 // One per context, created by the first fb_nes_init and reused by every later session: the device buffers only grow
@@ -54,3 +64,6 @@ struct FbNes {
 
 void fb_nes_destroy(fb_ctx *ctx);
 void fb_comm_info(fb_ctx *ctx, int *rank, int *world);
+struct FbNesDev;
+// fills the peer-exchange fields of `d` when the context has mapped peer buffers large enough for `count` doubles; bumps the session
+int fb_comm_p2p_attach(fb_ctx *ctx, FbNesDev *d, size_t count);

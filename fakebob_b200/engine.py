@@ -290,7 +290,7 @@ class GmmEngine:
         _lib.check(self.lib.fb_synchronize(self.h))
 
     # ---- multi-GPU ---------------------------------------------------------------------------------
-    def comm_init_from_torch(self):
+    def comm_init_from_torch(self, max_samples=1 << 20):
         """Create the NCCL communicator for this engine using torch.distributed for the id exchange."""
         import torch.distributed as dist
         rank, world = dist.get_rank(), dist.get_world_size()
@@ -303,6 +303,21 @@ class GmmEngine:
         dist.broadcast_object_list(obj, src=0)
         ident = (C.c_char * 128).from_buffer_copy(obj[0])
         _lib.check(self.lib.fb_comm_init(self.h, ident, rank, world))
+        # exchange buffers in peer memory (one node, <= 8 ranks): the gradient partials are then pulled over NVLink inside
+        # the update kernel; if the mapping is refused the ncclAllReduce path stays in use
+        self.p2p = False
+        if world <= 8 and os.environ.get("FB_NO_P2P") is None:
+            hbuf = (C.c_char * 64)()
+            _lib.check(self.lib.fb_comm_p2p_export(self.h, int(max_samples), hbuf))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(hbuf))
+            allh = (C.c_char * (64 * world)).from_buffer_copy(b"".join(handles))
+            ok = self.lib.fb_comm_p2p_import(self.h, allh) == 0
+            flags = [None] * world
+            dist.all_gather_object(flags, ok)
+            self.p2p = all(flags)
+            if not self.p2p:
+                os.environ["FB_NO_P2P"] = "1"          # every rank must take the same path
 
 
 class IvectorEngine(GmmEngine):

@@ -206,6 +206,14 @@ int fb_get_voiced_rows(fb_ctx *ctx, int *rows);
 int fb_comm_unique_id(void *out_128_bytes);
 int fb_comm_init(fb_ctx *ctx, const void *unique_id_128_bytes, int rank, int world);
 int fb_comm_destroy(fb_ctx *ctx);
+/* Optional, after fb_comm_init (<= 8 ranks of one node): exchange buffers in peer memory.  Every rank calls
+ * fb_comm_p2p_export (allocates its buffer for utterances of up to max_samples, returns a 64-byte CUDA IPC handle), the host
+ * gathers the handles of all ranks in rank order, every rank calls fb_comm_p2p_import.  From then on an iteration's
+ * gradient partials are published in each rank's own buffer and pulled over NVLink inside the update kernel (summed in rank
+ * order, identical on every rank) instead of going through ncclAllReduce.  FB_ERR_UNSUPPORTED (mapping refused): the
+ * ncclAllReduce path stays in use. */
+int fb_comm_p2p_export(fb_ctx *ctx, int64_t max_samples, void *handle_out_64_bytes);
+int fb_comm_p2p_import(fb_ctx *ctx, const void *handles_world_x_64_bytes);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
-"""Run under torchrun (one rank per GPU): S-sharded NES attack with the NCCL gradient all-reduce vs the
-single-GPU run of the same attack (same Philox stream).  Rank 0 prints the comparison."""
+"""Run under torchrun (one rank per GPU): S-sharded NES attack vs the single-GPU run of the same attack (same Philox stream),
+once with the one-shot peer-memory exchange (default) and once with the ncclAllReduce path (FB_NO_P2P semantics), then two
+back-to-back sessions of different length.  Rank 0 prints the comparison."""
 import os
 import sys
 import tempfile
@@ -39,18 +40,41 @@ def main():
         single = (fb1.final_adver.copy(), fb1.log.copy(), fb1.iters_done)
     dist.barrier()
     model._engine.comm_init_from_torch()
-    fbm = FakeBob("OSI", "untargeted", model, seed=123, verbose=False, **hp)
-    fbm.attack(audio, None, threshold=thr)
+    print("rank", rank, "peer-memory exchange:", model._engine.p2p, flush=True)
+    import time
+    results = {}
+    for mode in ("p2p", "nccl"):
+        if mode == "nccl":
+            os.environ["FB_NO_P2P"] = "1"           # fb_comm_p2p_attach checks it at every fb_nes_init
+        fbm = FakeBob("OSI", "untargeted", model, seed=123, verbose=False, **hp)
+        fbm.attack(audio, None, threshold=thr)
+        dist.barrier()
+        t0 = time.perf_counter()
+        fbt = FakeBob("OSI", "untargeted", model, seed=124, verbose=False, max_iter=200, samples_per_draw=16)
+        fbt.attack(audio, None, threshold=thr)
+        dt = time.perf_counter() - t0
+        advs = [None] * world
+        dist.all_gather_object(advs, fbm.final_adver)
+        results[mode] = (fbm.final_adver.copy(), fbm.log.copy())
+        if rank == 0:
+            same_across_ranks = all(np.array_equal(advs[0], a) for a in advs[1:])
+            a1, l1, n1 = single
+            print("[%s] world %d iters %d %d replicas identical: %s; 200-iteration attack %.1f it/s" % (mode, world, n1, fbm.iters_done, same_across_ranks, 200 / dt))
+            print("[%s] adver agreement single vs sharded: %.6f" % (mode, np.mean(a1 == fbm.final_adver)))
+            print("[%s] max |loss diff|: %.3e  max |final_loss diff|: %.3e" % (mode, np.abs(l1[:, 1] - fbm.log[:, 1]).max(), np.abs(l1[:, 2] - fbm.log[:, 2]).max()))
+            assert same_across_ranks and n1 == fbm.iters_done
+            assert np.mean(a1 == fbm.final_adver) > 0.999
+    os.environ.pop("FB_NO_P2P", None)
+    # a second, shorter utterance right after (new session number, other buffer sizes), still over peer memory
+    audio2 = synth.synth_utterance(42, 2, 16000)
+    fb2 = FakeBob("OSI", "untargeted", model, seed=7, verbose=False, max_iter=6, samples_per_draw=10)
+    fb2.attack(audio2, None, threshold=thr)
     advs = [None] * world
-    dist.all_gather_object(advs, fbm.final_adver)
+    dist.all_gather_object(advs, fb2.final_adver)
     if rank == 0:
-        same_across_ranks = all(np.array_equal(advs[0], a) for a in advs[1:])
-        a1, l1, n1 = single
-        print("world", world, "iters", n1, fbm.iters_done, "replicas identical:", same_across_ranks)
-        print("adver agreement single vs sharded: %.6f" % np.mean(a1 == fbm.final_adver))
-        print("max |loss diff|: %.3e  max |final_loss diff|: %.3e" % (np.abs(l1[:, 1] - fbm.log[:, 1]).max(), np.abs(l1[:, 2] - fbm.log[:, 2]).max()))
-        assert same_across_ranks and n1 == fbm.iters_done
-        assert np.mean(a1 == fbm.final_adver) > 0.999
+        assert all(np.array_equal(advs[0], a) for a in advs[1:]) and fb2.iters_done == 6
+        assert np.array_equal(results["p2p"][0], results["nccl"][0]) or np.mean(results["p2p"][0] == results["nccl"][0]) > 0.999
+        print("p2p vs nccl adversarial audio identical fraction: %.6f" % np.mean(results["p2p"][0] == results["nccl"][0]))
         print("MULTI_GPU_OK")
     dist.barrier()
     dist.destroy_process_group()
