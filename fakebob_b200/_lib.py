@@ -43,6 +43,7 @@ _SIGS = {
     "fb_set_stream": (C.c_int, [_P, _P]),
     "fb_synchronize": (C.c_int, [_P]),
     "fb_set_feature_config": (C.c_int, [_P, C.POINTER(FeatConfig)]),
+    "fb_set_kaldi_exact": (C.c_int, [_P, C.c_int, C.c_int]),
     "fb_load_diag_gmm": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "fb_finalize_gmms": (C.c_int, [_P, C.c_int]),
     "fb_set_gmm_delta_terms": (C.c_int, [_P, C.c_int]),

@@ -116,6 +116,14 @@ extern "C" int fb_set_feature_config(fb_ctx *ctx, const fb_feat_config *cfg) {
   return FB_OK;
 }
 
+extern "C" int fb_set_kaldi_exact(fb_ctx *ctx, int compress_features, int text_precision) {
+  FB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  ctx->kx_compress = compress_features != 0;
+  ctx->kx_text = text_precision != 0;
+  fb_bump_alloc_epoch();          // captured NES graphs hold the old kernel sequence / arguments
+  return FB_OK;
+}
+
 extern "C" int fb_set_gmm_delta_terms(fb_ctx *ctx, int terms) {
   FB_CHECK_ARG(ctx && terms >= 0 && terms <= 3, "terms must be 0 (automatic), 1, 2 or 3");
   ctx->delta_terms_req = terms;

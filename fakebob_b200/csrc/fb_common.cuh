@@ -127,6 +127,8 @@ struct fb_ctx {
   int64_t total_samples = 0;
   int total_frames = 0, max_frames = 0;
   bool debug_feats = false;
+  bool kx_compress = false;    // fb_set_kaldi_exact: CompressedMatrix round trip of the MFCCs
+  bool kx_text = false;        // fb_set_kaldi_exact: 7-significant-digit text round trip of scores / i-vectors
   DevBuf<int16_t> wave;
   DevBuf<int64_t> wave_off;    // B+1
   DevBuf<int>     frame_off;   // B+1
@@ -177,6 +179,34 @@ static inline bool fb_once_per_device(std::atomic<unsigned long long> &mask, int
   return (mask.fetch_or(bit) & bit) == 0;
 }
 static inline int fb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Kaldi's text output stream has precision(7): what survives writing a value and reading it back
+// (round to 7 significant decimal digits; double arithmetic, exact powers of ten up to 1e22)
+#ifdef __CUDACC__
+__host__ __device__ static inline double fb_round_sig7(double v) {
+  if (v == 0.0 || !(fabs(v) < 1e300)) return v;
+  int e = (int)floor(log10(fabs(v)));
+  int p = 6 - e;
+  if (p > 22 || p < -22) return v;
+  const double s = pow(10.0, (double)(p < 0 ? -p : p));
+  double r = (p >= 0) ? rint(v * s) / s : rint(v / s) * s;
+  // log10 may land one decade off right at a power of ten: the result then has 8 or 6 digits, fix by one retry
+  if (fabs(r) >= pow(10.0, (double)(e + 1))) { ++e; p = 6 - e; const double s2 = pow(10.0, (double)(p < 0 ? -p : p)); r = (p >= 0) ? rint(v * s2) / s2 : rint(v / s2) * s2; }
+  return r;
+}
+#endif
+
+// ---- NVTX ranges around the enqueue of every stage (header-only NVTX3: no cost unless a tool is attached) ---------------
+#include <nvtx3/nvToolsExt.h>
+struct FbNvtxSeq {
+  bool open = false;
+  void next(const char *name) {
+    if (open) nvtxRangePop();
+    nvtxRangePushA(name);
+    open = true;
+  }
+  ~FbNvtxSeq() { if (open) nvtxRangePop(); }
+};
 
 // ---- programmatic dependent launch ---------------------------------------------------------------------------------
 // Every kernel of the scoring / NES sequence is launched with the programmatic-stream-serialization attribute and starts

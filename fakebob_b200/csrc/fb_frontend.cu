@@ -294,6 +294,92 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kaldi-exact mode: CompressedMatrix (speech-feature format) round trip of one utterance's MFCC matrix, in place.
+// matrix/compressed-matrix.cc: global min / range; per column the values at sorted positions 0, T/4, 3(T/4), T-1 as
+// uint16 (forced strictly increasing); every value as one byte, piecewise linear between those four points.
+// One CTA per utterance; the order statistics by rank counting (T ~ 500, not a hot path).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cm_float_to_u16(float vmin, float vrange, float v) {
+  float f = __fdiv_rn(__fadd_rn(v, -vmin), vrange);
+  f = fminf(fmaxf(f, 0.f), 1.f);
+  return (int)__fadd_rn(__fmul_rn(f, 65535.0f), 0.499f);
+}
+__device__ __forceinline__ float cm_u16_to_float(float vmin, float vrange, int u) {
+  return __fadd_rn(vmin, __fmul_rn(__fmul_rn(vrange, 1.52590218966964e-05f), (float)u));
+}
+
+__global__ void __launch_bounds__(256)
+mfcc_compress_kernel(float *__restrict__ mfcc, const int *__restrict__ frame_off, int *__restrict__ err, const int *__restrict__ done_flag) {
+  FB_GRID_DEP_SYNC();
+  if (done_flag && *done_flag) return;
+  __shared__ float s_mn[8], s_mx[8];
+  __shared__ float s_q[4];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f0 = frame_off[b];
+  const int T = frame_off[b + 1] - f0;
+  float *M = mfcc + (size_t)f0 * FB_NCEPS;
+  if (T <= 8) {                                   // Kaldi would pick the two-byte format: not implemented
+    if (tid == 0) atomicExch(err, 2);
+    return;
+  }
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = tid; i < T * FB_NCEPS; i += 256) { const float v = M[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  mn = s_mn[0]; mx = s_mx[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) { mn = fminf(mn, s_mn[i]); mx = fmaxf(mx, s_mx[i]); }
+  if (mx == mn) mx = __fadd_rn(mn, __fadd_rn(1.0f, fabsf(mn)));
+  const float vmin = mn, vrange = __fadd_rn(mx, -mn);
+  const int q = T / 4;
+  for (int d = 0; d < FB_NCEPS; ++d) {
+    __syncthreads();
+    // the values at sorted positions 0, q, 3q, T-1: an element's position = #smaller + #equal with a lower index
+    for (int i = tid; i < T; i += 256) {
+      const float v = M[(size_t)i * FB_NCEPS + d];
+      int rank = 0;
+      for (int j = 0; j < T; ++j) {
+        const float w = M[(size_t)j * FB_NCEPS + d];
+        rank += (w < v || (w == v && j < i)) ? 1 : 0;
+      }
+      if (rank == 0) s_q[0] = v;
+      if (rank == q) s_q[1] = v;
+      if (rank == 3 * q) s_q[2] = v;
+      if (rank == T - 1) s_q[3] = v;
+    }
+    __syncthreads();
+    const int p0 = min(cm_float_to_u16(vmin, vrange, s_q[0]), 65532);
+    const int p25 = min(max(cm_float_to_u16(vmin, vrange, s_q[1]), p0 + 1), 65533);
+    const int p75 = min(max(cm_float_to_u16(vmin, vrange, s_q[2]), p25 + 1), 65534);
+    const int p100 = max(cm_float_to_u16(vmin, vrange, s_q[3]), p75 + 1);
+    const float g0 = cm_u16_to_float(vmin, vrange, p0), g25 = cm_u16_to_float(vmin, vrange, p25);
+    const float g75 = cm_u16_to_float(vmin, vrange, p75), g100 = cm_u16_to_float(vmin, vrange, p100);
+    __syncthreads();                              // every rank pass of this column has finished reading it
+    for (int i = tid; i < T; i += 256) {
+      const float v = M[(size_t)i * FB_NCEPS + d];
+      int c;
+      if (v < g25) {
+        const float f = __fdiv_rn(__fadd_rn(v, -g0), __fadd_rn(g25, -g0));
+        c = min(max((int)__fadd_rn(__fmul_rn(f, 64.f), 0.5f), 0), 64);
+      } else if (v < g75) {
+        const float f = __fdiv_rn(__fadd_rn(v, -g25), __fadd_rn(g75, -g25));
+        c = 64 + min(max((int)__fadd_rn(__fmul_rn(f, 128.f), 0.5f), 0), 128);
+      } else {
+        const float f = __fdiv_rn(__fadd_rn(v, -g75), __fadd_rn(g100, -g75));
+        c = 192 + min(max((int)__fadd_rn(__fmul_rn(f, 63.f), 0.5f), 0), 63);
+      }
+      float o;
+      if (c <= 64) o = __fadd_rn(g0, __fmul_rn(__fmul_rn(__fadd_rn(g25, -g0), (float)c), 1.0f / 64.0f));
+      else if (c <= 192) o = __fadd_rn(g25, __fmul_rn(__fmul_rn(__fadd_rn(g75, -g25), (float)(c - 64)), 1.0f / 128.0f));
+      else o = __fadd_rn(g75, __fmul_rn(__fmul_rn(__fadd_rn(g100, -g75), (float)(c - 192)), 1.0f / 63.0f));
+      M[(size_t)i * FB_NCEPS + d] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // VAD + per-utterance voiced ranks + cross-utterance row offsets (last CTA done performs the scan).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -615,14 +701,23 @@ int fb_run_frontend_flag(fb_ctx *ctx, const int *done_flag) {
   int rc;
   if ((rc = fb_prepare_tables(ctx))) return rc;
   const int B = ctx->B;
+  FbNvtxSeq nv;
+  nv.next("fb:mfcc");
   dim3 g1(fb_div_up(ctx->max_frames, MFCC_WARPS), B);
   FB_CUDA(fb_launch(mfcc_kernel, g1, dim3(MFCC_WARPS * 32), 0, ctx->stream, ctx->wave.p, ctx->wave_off.p, ctx->frame_off.p,
                     ctx->tables_dev, ctx->mfcc.p, done_flag));
+  if (ctx->kx_compress) {      // Kaldi-exact mode: copy-feats --compress=true round trip before anything reads the MFCCs
+    nv.next("fb:mfcc_compress");
+    FB_CUDA(fb_launch(mfcc_compress_kernel, dim3(B), dim3(256), 0, ctx->stream, ctx->mfcc.p, ctx->frame_off.p, ctx->misc.p + 1, done_flag));
+    ctx->launches += 1;
+  }
   fb_prof_mark(ctx, 1);
+  nv.next("fb:vad_scan");
   const int c0_cap = ctx->max_frames < 8192 ? ctx->max_frames : 8192;
   FB_CUDA(fb_launch(vad_scan_kernel, dim3(B), dim3(256), (size_t)c0_cap * sizeof(float), ctx->stream, ctx->mfcc.p, ctx->frame_off.p,
                     ctx->tables_dev, ctx->vrank.p, ctx->nvoiced.p, ctx->row_off.p, ctx->misc.p, B, c0_cap, done_flag));
   fb_prof_mark(ctx, 2);
+  nv.next("fb:feats");
   const size_t smem = fb_feats_smem_bytes(ctx->max_frames);
   const int use_smem = smem <= FB_FEATS_SMEM_MAX;
   static std::atomic<unsigned long long> configured_mask{0};

@@ -708,7 +708,7 @@ gmm_frame_kernel(const float2 *__restrict__ part, const int *__restrict__ misc, 
 
 __global__ void __launch_bounds__(128)
 gmm_reduce_kernel(const float *__restrict__ frame_ll, const int *__restrict__ row_off, double *__restrict__ avg_ll,
-                  int n_models, int rows_cap, const int *__restrict__ done_flag) {
+                  int n_models, int rows_cap, const int *__restrict__ done_flag, int text7) {
   FB_GRID_DEP_SYNC();
   if (done_flag && *done_flag) return;
   __shared__ double s_red[4];
@@ -723,7 +723,9 @@ gmm_reduce_kernel(const float *__restrict__ frame_ll, const int *__restrict__ ro
   if (threadIdx.x == 0) {
     const double tot = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
     const int n = r1 - r0;
-    avg_ll[(size_t)b * n_models + model] = (n > 0) ? (double)__fdiv_rn((float)tot, (float)n) : 0.0;
+    double a = (n > 0) ? (double)__fdiv_rn((float)tot, (float)n) : 0.0;
+    if (text7) a = fb_round_sig7(a);               // the reference parses this number from 7-digit text
+    avg_ll[(size_t)b * n_models + model] = a;
   }
 }
 
@@ -910,6 +912,8 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
   FB_CHECK_ARG(ctx->n_models > 0, "no GMMs loaded (fb_finalize_gmms)");
   const int nst = ctx->C / FB_STAGE_N;
   int umma_grid = 0;
+  FbNvtxSeq nv;
+  nv.next("fb:gmm_umma");
   {
     GmmArgs a;
     a.a_img = ctx->a_img.p;
@@ -931,10 +935,11 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     else FB_CUDA(fb_launch(gmm_umma_kernel<false, false>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
   }
   fb_prof_mark(ctx, 4);
+  nv.next("fb:gmm_frame_reduce");
   FB_CUDA(fb_launch(gmm_frame_kernel, dim3(fb_div_up(ctx->total_frames, 128), ctx->n_models), dim3(128), 0, ctx->stream,
                     ctx->part.p, ctx->misc.p, ctx->frame_ll.p, nst, ctx->rows_cap, done_flag, umma_grid, ctx->gmm_shared ? 1 : ctx->n_models));
   FB_CUDA(fb_launch(gmm_reduce_kernel, dim3(ctx->B, ctx->n_models), dim3(128), 0, ctx->stream, ctx->frame_ll.p, ctx->row_off.p,
-                    ctx->avg_ll.p, ctx->n_models, ctx->rows_cap, done_flag));
+                    ctx->avg_ll.p, ctx->n_models, ctx->rows_cap, done_flag, ctx->kx_text ? 1 : 0));
   fb_prof_mark(ctx, 5);
   ctx->launches += 3;
   FB_CUDA(cudaGetLastError());
@@ -961,6 +966,8 @@ int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag) {
   int grid = ctx->num_sms;
   if (max_units < grid) grid = (int)max_units;
   FB_CHECK_ARG(!ctx->gmm_shared, "Gaussian selection needs the general W image");
+  FbNvtxSeq nv;
+  nv.next("fb:gmm_umma_store");
   FB_CUDA(fb_launch(gmm_umma_kernel<true, false>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
   fb_prof_mark(ctx, 4);
   ctx->launches += 1;

@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(256)
 plda_kernel(const float *__restrict__ ivec, const float *__restrict__ mean_vec, const float *__restrict__ lda, int lda_cols,
             const double *__restrict__ plda_T, const double *__restrict__ plda_off, const double *__restrict__ psi,
             const double *__restrict__ u_train, int R, int L, int K, double *__restrict__ scores,
-            const int *__restrict__ done_flag) {
+            const int *__restrict__ done_flag, int text7) {
   if (done_flag && *done_flag) return;
   extern __shared__ double s_d[];
   double *u = s_d;                                   // [L]
@@ -942,7 +942,12 @@ plda_kernel(const float *__restrict__ ivec, const float *__restrict__ mean_vec, 
   __shared__ double s_red[8];
   __shared__ double s_bcast;
   const int b = blockIdx.x, tid = threadIdx.x;
-  for (int r = tid; r < R; r += blockDim.x) v[r] = __fadd_rn(ivec[(size_t)b * R + r], -mean_vec[r]);
+  // Kaldi-exact text mode: the i-vector reaches the back-end through `ark,t:` (7 significant digits, read back as float)
+  for (int r = tid; r < R; r += blockDim.x) {
+    float w = ivec[(size_t)b * R + r];
+    if (text7) w = (float)fb_round_sig7((double)w);
+    v[r] = __fadd_rn(w, -mean_vec[r]);
+  }
   __syncthreads();
   for (int l = tid; l < L; l += blockDim.x) {
     float acc = (lda_cols == R + 1) ? lda[(size_t)l * lda_cols + R] : 0.f;
@@ -1009,7 +1014,10 @@ plda_kernel(const float *__restrict__ ivec, const float *__restrict__ mean_vec, 
       given += __shfl_xor_sync(0xffffffffu, given, o);
       without += __shfl_xor_sync(0xffffffffu, without, o);
     }
-    if (lane == 0) scores[(size_t)b * K + k] = -0.5 * given + 0.5 * without;
+    if (lane == 0) {
+      const double llr = -0.5 * given + 0.5 * without;
+      scores[(size_t)b * K + k] = text7 ? fb_round_sig7(llr) : llr;
+    }
   }
 }
 
@@ -1246,8 +1254,11 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   const int B = ctx->B;
   const int rows = ctx->total_frames;           // upper bound of the voiced rows (device knows the exact count)
   if ((rc = fb_run_gmm_store(ctx, v->ll.p, done_flag))) return rc;
+  FbNvtxSeq nv;
+  nv.next("fb:gselect");
   gselect_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(v->ll.p, ctx->misc.p, v->C, v->gsel.p, done_flag);
   fb_prof_mark(ctx, 8);
+  nv.next("fb:fgmm_post");
   static const bool plain_post = getenv("FB_IV_PLAIN_POST") != nullptr;       // diagnostic: the one-row-per-warp kernel
   if (plain_post) {
     fgmm_post_kernel<<<fb_div_up(rows, 8), 256, 0, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->gconsts.p, v->means_invcovars.p,
@@ -1260,6 +1271,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
         ctx->vrank.p, ctx->row_off.p, B, v->C, n_chunks, v->min_post, v->post.p, done_flag);
   }
   fb_prof_mark(ctx, 9);
+  nv.next("fb:ivec_stats");
   // bucket capacity: the longest utterance, or as many frames as fit in shared memory (longer utterances go in chunks)
   const size_t smem_fixed = (size_t)(3 * v->C + 1) * sizeof(int) + 2 * sizeof(unsigned short) + 16;
   const int cap_frames = (int)((220 * 1024 - smem_fixed) / (IV_NSEL * 12));
@@ -1274,15 +1286,18 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   ivec_stats_kernel<<<dim3(B, IV_STATS_SPLIT), IV_STATS_THREADS, smem_stats, ctx->stream>>>(ctx->feats_f32.p, v->gsel.p, v->post.p, ctx->row_off.p, v->C, max_pairs,
                                                          v->gamma.p, v->Xs.p, ctx->misc.p + 1, done_flag);
   fb_prof_mark(ctx, 10);
+  nv.next("fb:ivec_lin");
   const int bch = fb_div_up(B, IV_BCHUNK);
   const int lin_threads = ((4 * ((v->R + 3) / 4) + 31) / 32) * 32;
   ivec_active_kernel<<<bch, 1024, 0, ctx->stream>>>(v->gamma.p, B, v->C, v->act_list.p, done_flag);
   ivec_lin_kernel<<<dim3(v->n_splits, bch), lin_threads, 0, ctx->stream>>>(v->sim32.p, v->Xs.p, v->act_list.p, B, v->C, v->R,
                                                                           v->n_splits, v->lin_part.p, done_flag);
   fb_prof_mark(ctx, 11);
+  nv.next("fb:ivec_quad");
   ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, v->act_list.p, B, v->C,
                                                                                    v->n_packed, v->quad.p, done_flag);
   fb_prof_mark(ctx, 12);
+  nv.next("fb:ivec_solve");
   const size_t smem_solve = (2 * (size_t)v->R + ((size_t)v->R + 2) * IV_PSTRIDE) * sizeof(double);
   static std::atomic<unsigned long long> attr_solve_mask{0};
   if (fb_once_per_device(attr_solve_mask, ctx->device)) {
@@ -1307,9 +1322,10 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   fb_prof_mark(ctx, 13);
   ctx->launches += 7;
   if (with_plda) {
+    nv.next("fb:plda");
     const size_t smem_plda = (size_t)v->L * sizeof(double) + (size_t)(v->R + v->L) * sizeof(float) + 16;
     plda_kernel<<<B, 256, smem_plda, ctx->stream>>>(v->ivec.p, v->mean_vec.p, v->lda.p, v->lda_cols, v->plda_T.p, v->plda_off.p,
-                                                    v->psi.p, v->u_train.p, v->R, v->L, v->K, v->scores.p, done_flag);
+                                                    v->psi.p, v->u_train.p, v->R, v->L, v->K, v->scores.p, done_flag, ctx->kx_text ? 1 : 0);
     ctx->launches += 1;
   }
   fb_prof_mark(ctx, 14);
@@ -1341,7 +1357,10 @@ extern "C" int fb_score_ivector_host(fb_ctx *ctx, const int16_t *wave, const int
     FB_CUDA(cudaMemcpyAsync(out_scores, v->scores.p, (size_t)B * v->K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (out_ivectors)
     FB_CUDA(cudaMemcpyAsync(out_ivectors, v->ivec.p, (size_t)B * v->R * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  return iv_check(ctx);
+  int rc2 = iv_check(ctx);
+  if (rc2 == FB_OK && out_ivectors && ctx->kx_text)          // what a reader of ivector-extract's text archive gets
+    for (size_t i = 0; i < (size_t)B * v->R; ++i) out_ivectors[i] = (float)fb_round_sig7((double)out_ivectors[i]);
+  return rc2;
 }
 
 extern "C" int fb_get_ivector_stats(fb_ctx *ctx, int b, double *gamma_host, double *x_host, double *lin_host, double *quad_host) {

@@ -691,9 +691,12 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
   int rc;
   dim3 gp(fb_div_up(fb_div_up(s->N, 4), 256), s->pairs_local > 0 ? (s->pairs_local < 8 ? s->pairs_local : 8) : 1);
   fb_prof_mark(ctx, -1);
+  FbNvtxSeq nv;
+  nv.next("fb:nes_perturb");
   FB_CUDA(fb_launch(perturb_kernel, gp, dim3(256), 0, ctx->stream, d, ctx->wave.p, s->N, philox));
   fb_prof_mark(ctx, 0);
   ctx->launches += 1;
+  nv.next("fb:nes_score");
   if ((rc = fb_run_frontend_flag(ctx, d.flags))) return rc;
   const double *ll_dev;
   int ll_stride;
@@ -707,6 +710,7 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
     ll_stride = ctx->n_models;
   }
   const int multi = s->world > 1;
+  nv.next("fb:nes_loss");
   if (multi) {
     FB_CUDA(fb_launch(nes_zero_red_kernel, dim3(1), dim3(256), 0, ctx->stream, d));
     ctx->launches += 1;
@@ -715,6 +719,7 @@ static int nes_enqueue_iteration(fb_ctx *ctx, int mode_get_grad) {
   fb_prof_mark(ctx, 6);
   ctx->launches += 1;
   const int nb = fb_div_up(s->N, 128);
+  nv.next(multi ? "fb:nes_exchange_update" : "fb:nes_update");
   if (!multi) {
     if (d.S >= 8 && d.S <= 128)
       FB_CUDA(fb_launch(nes_update8_kernel, dim3(fb_div_up(s->N, 128)), dim3(128), 0, ctx->stream, d, mode_get_grad ? 3 : 0));

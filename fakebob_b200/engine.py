@@ -77,6 +77,7 @@ class GmmEngine:
             delta_terms = int(os.environ.get("FAKEBOB_GMM_DELTA_TERMS", "0"))
         _lib.check(self.lib.fb_set_gmm_delta_terms(self.h, int(delta_terms)))
         _lib.check(self.lib.fb_finalize_gmms(self.h, self.n_models))
+        self._kaldi_exact_from_env()
         self._nes_keep = None
         self._last_B = 0
 
@@ -133,6 +134,18 @@ class GmmEngine:
         self._last_offsets = offsets
         return {"weights": np.array(g["weights"], dtype=np.float32), "means_invvars": miv,
                 "inv_vars": np.array(g["inv_vars"], dtype=np.float32), "gconsts": gc, "occupancy": occ}
+
+    def set_kaldi_exact(self, compress=False, text=False):
+        """Non-ideal effects of the reference's real Kaldi path: CompressedMatrix round trip of the MFCCs
+        (copy-feats --compress=true) and 7-significant-digit text round trips of scores / i-vectors.  Off by default;
+        the scorers switch them on from FAKEBOB_KALDI_EXACT="compress,text"."""
+        _lib.check(self.lib.fb_set_kaldi_exact(self.h, 1 if compress else 0, 1 if text else 0))
+
+    def _kaldi_exact_from_env(self):
+        opt = os.environ.get("FAKEBOB_KALDI_EXACT", "")
+        if opt:
+            o = {x.strip() for x in opt.replace("1", "compress,text").split(",")}
+            self.set_kaldi_exact("compress" in o, "text" in o)
 
     def set_debug(self, on=True):
         _lib.check(self.lib.fb_set_debug(self.h, 1 if on else 0))
@@ -361,6 +374,7 @@ class IvectorEngine(GmmEngine):
                                                  _ptr(np.ascontiguousarray(pl["psi"])), self.R, self.L))
         self.n_models = 1
         self.K = 0
+        self._kaldi_exact_from_env()
         self._nes_keep = None
         self._last_B = 0
 

@@ -63,6 +63,14 @@ typedef struct fb_feat_config {
   int   cmn_window;            /* 300 */
 } fb_feat_config;
 int fb_set_feature_config(fb_ctx *ctx, const fb_feat_config *cfg);
+/* Non-ideal effects of the reference's real Kaldi path, off by default:
+ *   compress_features != 0: the MFCC matrix of every utterance goes through Kaldi's CompressedMatrix speech-feature codec
+ *     (steps/make_mfcc.sh writes with copy-feats --compress=true, gmm_ubm_kaldiHelper.py:138-147) before VAD / deltas / CMN;
+ *   text_precision != 0: the values the reference parses from Kaldi's text output are rounded to 7 significant digits:
+ *     average log-likelihoods (ark,t:, gmm_ubm_kaldiHelper.py:204-208), i-vectors and PLDA scores
+ *     (ivector_PLDA_kaldiHelper.py:202-211,262-271).
+ * Kaldi's default dither (libc rand() noise of +-1 LSB per sample) is not reproduced on the device. */
+int fb_set_kaldi_exact(fb_ctx *ctx, int compress_features, int text_precision);
 
 /* ---- diagonal GMMs ---------------------------------------------------------------
  * Replaces: the model rxfilename argument of gmm-global-get-frame-likes

@@ -145,14 +145,15 @@ def extract_frames(wave, cfg):
     return wave[idx]
 
 
-def mfcc(wave, cfg=None, rng=None):
-    """compute-mfcc-feats: int16-valued samples -> (T, num_ceps) float32 (use_energy, raw_energy)."""
+def mfcc(wave, cfg=None, rng=None, frames=None):
+    """compute-mfcc-feats: int16-valued samples -> (T, num_ceps) float32 (use_energy, raw_energy).
+    frames: already extracted (T, L) windows, e.g. with Kaldi's libc dither applied (oracle.kaldi_nonideal.dither_frames)."""
     cfg = cfg or FeatConfig()
-    fr = extract_frames(wave, cfg)                       # (T, L) f32
+    fr = extract_frames(wave, cfg) if frames is None else np.asarray(frames, dtype=F32)   # (T, L) f32
     T, L = fr.shape
     if T == 0:
         return np.zeros((0, cfg.num_ceps), dtype=F32)
-    if cfg.dither != 0.0:
+    if cfg.dither != 0.0 and frames is None:
         rng = rng or np.random.default_rng(0)
         fr = (fr + F32(cfg.dither) * rng.standard_normal(fr.shape).astype(F32)).astype(F32)
     # remove_dc_offset: Sum() in double, cast to float, / L in float
