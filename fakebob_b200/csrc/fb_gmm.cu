@@ -111,6 +111,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
+// Waiting warps must not steal issue slots from the epilogue warps of their scheduler (ncu: 45.8 M warp instructions per
+// launch, issue slots 47 % busy, while the epilogue -- the bottleneck -- needs ~26 M): the suspend-time hint lets the
+// hardware park the warp until the phase completes or the hint expires instead of re-issuing try_wait in a tight loop.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+  } while (!done);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -283,9 +297,17 @@ extern "C" int fb_debug_gmm_stats(long long *out_host) {
 }
 #define STAT_DECL(x) long long x = 0
 #define STAT_WAIT(acc, bar, par) do { const long long t_ = clock64(); mbar_wait(bar, par); acc += clock64() - t_; } while (0)
+#define STAT_WAIT_PARKED(acc, bar, par, ns) do { const long long t_ = clock64(); mbar_wait_parked(bar, par, ns); acc += clock64() - t_; } while (0)
 #else
 #define STAT_DECL(x)
 #define STAT_WAIT(acc, bar, par) mbar_wait(bar, par)
+#define STAT_WAIT_PARKED(acc, bar, par, ns) mbar_wait_parked(bar, par, ns)
+#endif
+#ifndef GMM_PARK_PRODUCER_NS
+#define GMM_PARK_PRODUCER_NS 2000
+#endif
+#ifndef GMM_PARK_ISSUER_NS
+#define GMM_PARK_ISSUER_NS 400
 #endif
 template <bool kStore, bool kShared>
 __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
@@ -365,7 +387,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
         for (int e = 0; e < 4; ++e) {          // tile0 hi, tile0 lo, tile1 hi, tile1 lo
           const uint32_t slot = cnt % kNumSlots;
-          STAT_WAIT(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+          STAT_WAIT_PARKED(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1, GMM_PARK_PRODUCER_NS);
           if (elect_one()) {
             mbar_expect_tx(bar_full + 8 * slot, kAHalfBytes);
             bulk_g2s(base + slot * kSlotBytes, src + (size_t)e * kAHalfBytes, kAHalfBytes, bar_full + 8 * slot);
@@ -383,7 +405,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #pragma unroll 1
         for (int e = -1; e * (int)SL.group < n_delta; ++e) {
           const uint32_t slot = cnt % kNumSlots;
-          STAT_WAIT(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+          STAT_WAIT_PARKED(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1, GMM_PARK_PRODUCER_NS);
           if (elect_one()) {
             uint32_t bytes, off;
             if (e < 0) { bytes = 40960u; off = 0; }
@@ -401,7 +423,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
         }
       } else {
         const uint32_t slot = cnt % kNumSlots;
-        STAT_WAIT(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1);
+        STAT_WAIT_PARKED(st_prod_empty, bar_empty + 8 * slot, ((cnt / kNumSlots) & 1) ^ 1, GMM_PARK_PRODUCER_NS);
         if (elect_one()) {
           const size_t off = ((size_t)model * (g.C / FB_STAGE_N) + stage) * (size_t)kWStageBytes;
           mbar_expect_tx(bar_full + 8 * slot, kWStageBytes);
@@ -472,11 +494,11 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
               sub_off = r * SL.dbytes; mask = SL.mask;
             }
           }
-          if (first_in_slot) STAT_WAIT(st_mma_full, bar_full + 8 * slot, (cnt / kNumSlots) & 1);
+          if (first_in_slot) STAT_WAIT_PARKED(st_mma_full, bar_full + 8 * slot, (cnt / kNumSlots) & 1, GMM_PARK_ISSUER_NS);
           const uint64_t w_hi = desc_w + (uint64_t)(((base + slot * kSlotBytes + sub_off) & 0x3FFFFu) >> 4);
           const uint32_t abuf = job % kNumAcc;
           // accumulator abuf was last used by job - 3, a job of the other tile: wait until that tile's epilogue has read it
-          if (job >= kNumAcc) STAT_WAIT(st_mma_acc, bar_acc_empty + 8 * (2 * abuf + (tile ^ 1)), ((job - kNumAcc) / (2 * kNumAcc)) & 1);
+          if (job >= kNumAcc) STAT_WAIT_PARKED(st_mma_acc, bar_acc_empty + 8 * (2 * abuf + (tile ^ 1)), ((job - kNumAcc) / (2 * kNumAcc)) & 1, GMM_PARK_ISSUER_NS);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_hi = tmem_base + kTmemA + tile * kTmemATileCols;

@@ -6,7 +6,7 @@ mkdir -p $FB_TREE_ROOT gpurun_out
 {
 python scripts/gmm_time.py
 for lib in "" $(ls fakebob_b200/libfb_*.so 2>/dev/null); do
-  for t in 1 3; do
+  for t in 2; do
     echo "== lib=${lib:-default} terms=$t"
     if [[ "$lib" == *stats* ]]; then
       FB_LIB_PATH=$PWD/$lib FAKEBOB_GMM_DELTA_TERMS=$t python scripts/gmm_stats.py
