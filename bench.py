@@ -371,6 +371,11 @@ def rooflines(name, prof, rows, n_models, peaks, active_frac=None, b_local=None)
             "bytes = active components x 72 x R x 4 (fp32 Sigma^-1 M rows of the components with gamma != 0; %.0f %% active)" % (100 * af))
         mem("ivec_quad", 4.0 * N_MIX * (IV_R * (IV_R + 1) // 2) * af, "ivec_quad_kernel",
             "bytes = active components x R(R+1)/2 x 4 (fp32 U rows of the components with gamma != 0; %.0f %% active)" % (100 * af))
+        tensor("fgmm_post", 2.0 * rows * 20 * (72 * 73 // 2 + 72), "fgmm_post_group_kernel",
+               "20 full-covariance log-likelihoods per frame, 2*rows*20*(D(D+1)/2+D) FLOP; CUDA-core kernel, tensor peak shown for scale")
+        mem("ivec_solve", 8.0 * B * (IV_R * (IV_R + 1) // 2) + 8.0 * B * IV_R * 2, "ivec_solve_kernel",
+            "latency-bound blocked Cholesky in float64 (B*R^3/3 = %.2f GFLOP); bytes = packed posterior precision read + lin + solution" % (B * IV_R ** 3 / 3e9))
+        mem("gselect", 4.0 * rows * N_MIX, "gselect_kernel", "bytes = component log-likelihoods read (rows x C x 4)")
     mem("mfcc", 2.0 * B * N_SAMPLES + 4.0 * B * (N_SAMPLES // 160) * 24, "mfcc_kernel", "bytes = int16 wave read + MFCC written (issue-bound kernel)")
     mem("feats", 4.0 * B * (N_SAMPLES // 160) * 24 + 2.0 * rows * 160 * 2, "feats_kernel", "bytes = MFCC read + fp16 hi/lo operand image written")
     return out, ms

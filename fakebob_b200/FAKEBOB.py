@@ -12,8 +12,11 @@ Differences a caller can see, all deliberate:
     generator whose seed is taken from numpy's global generator at construction, so ``np.random.seed``
     still makes runs reproducible; "numpy" reproduces the reference's stream exactly
     (``np.random.normal(size=(N, S//2))`` per iteration, FAKEBOB.py:234) at ~90 ms/iteration of host time.
-  * ``model`` must be one of this package's scorers (they carry the resident device models); arbitrary
-    duck-typed black boxes are what the reference's own FAKEBOB.py is for.
+  * ``model`` is normally one of this package's scorers (they carry the resident device models and the whole iteration
+    then stays on the GPU).  Any other object with the reference's ``score()`` / ``make_decisions()`` interface
+    (README.md:136, a black-box system) is attacked with the same device loop, except that the S+1 audios of each iteration
+    are handed to ``model.score()`` on the host as int16-exact float audio (what the reference's own scorers quantise them to,
+    gmm_ubm_OSI.py:83-85) and the scores are handed back; this mode uses the Philox noise stream.
   * per-iteration prints are emitted after each batch of ``iters_per_launch`` iterations.
 """
 import os
@@ -31,9 +34,10 @@ class FakeBob(object):
     def __init__(self, task, attack_type, model, adver_thresh=0., epsilon=0.002, max_iter=1000,
                  max_lr=0.001, min_lr=1e-6, samples_per_draw=50, sigma=0.001, momentum=0.9,
                  plateau_length=5, plateau_drop=2., *, rng=None, seed=None, verbose=None, iters_per_launch=32):
-        if not hasattr(model, "_engine"):
-            raise TypeError("fakebob_b200.FakeBob needs one of this package's device-backed scorers "
-                            "(gmm_CSI/gmm_OSI/gmm_SV/iv_*); there is no CPU fallback for black-box models")
+        if not (hasattr(model, "score") and hasattr(model, "make_decisions")):
+            raise TypeError("model must provide score() and make_decisions() (reference README.md:136)")
+        self._external = not hasattr(model, "_engine")
+        self._ext_engine = None
         self.task = task
         self.attack_type = attack_type
         self.model = model
@@ -50,6 +54,8 @@ class FakeBob(object):
         self.rng = rng or os.environ.get("FAKEBOB_RNG", "philox")
         if self.rng not in ("philox", "numpy"):
             raise ValueError("rng must be 'philox' or 'numpy'")
+        if self._external and self.rng != "philox":
+            raise ValueError("black-box models are attacked with the device noise generator (rng='philox')")
         # the Philox key comes from numpy's global generator (so np.random.seed still makes runs reproducible); in 'numpy'
         # mode nothing is drawn here, so the per-iteration np.random.normal stream is exactly the reference's
         if seed is not None:
@@ -83,6 +89,16 @@ class FakeBob(object):
 
     def _nes_init(self, audio, max_iter):
         m = self.model
+        if self._external:
+            from .engine import ExternalEngine
+            if self._ext_engine is None:
+                self._ext_engine = ExternalEngine()
+            eng = self._ext_engine
+            eng.nes_init(audio, self.task, self.attack_type, self._n_speakers(audio), self._label(), self.threshold,
+                         self.adver_thresh, self.epsilon, max_iter, self.max_lr, self.min_lr, self.samples_per_draw,
+                         self.sigma, self.momentum, self.plateau_length, self.plateau_drop, rng="philox", seed=self.seed,
+                         draw_base=self.draws, external=True)
+            return eng
         eng = m._engine
         zm = getattr(m, "z_norm_means", None) if self.task == "CSI" or m._fb_arch == "iv" else None
         zs = getattr(m, "z_norm_stds", None) if zm is not None else None
@@ -91,6 +107,22 @@ class FakeBob(object):
                      self.samples_per_draw, self.sigma, self.momentum, self.plateau_length, self.plateau_drop,
                      rng=self.rng, seed=self.seed, draw_base=self.draws, z_means=zm, z_stds=zs)
         return eng
+
+    def _n_speakers(self, audio):
+        """Black-box models: the number of enrolled speakers is what score() returns per audio."""
+        if self.task == "SV":
+            return 1
+        n = getattr(self.model, "n_speakers", None)
+        if n is None:
+            n = int(np.asarray(self.model.score(audio)).reshape(-1).shape[0])
+        return n
+
+    def _ext_scores(self, eng, kw):
+        """One batch through a black-box scorer: (S+1, N) int16 from the device -> model.score((N, S+1) float) -> (S+1, K)."""
+        wave = eng.nes_ext_perturb()
+        audios = np.ascontiguousarray(wave.T.astype(np.float64) / 32768.0)
+        sc = np.asarray(self.model.score(audios, **kw), dtype=np.float64)
+        return sc.reshape(wave.shape[0], -1)
 
     def _host_noise(self, n):
         """The reference's draw (FAKEBOB.py:234), re-laid-out pair-major for the device."""
@@ -115,13 +147,17 @@ class FakeBob(object):
         self.poll_times = [t_start - t_init]         # seconds: fb_nes_init, then one entry per polled batch of iterations
         done, stopped, printed = 0, 0, 0
         chunk = 1 if self.rng == "numpy" else self.iters_per_launch
+        kw_score = dict(fs=fs, bits_per_sample=bits_per_sample, n_jobs=n_jobs, debug=debug)
         while not stopped and done < self.max_iter:
             k = min(chunk, self.max_iter - done)
             noise = None
             if self.rng == "numpy":
                 noise = np.stack([self._host_noise(n) for _ in range(k)])
             t_poll = time.time()
-            eng.nes_run(k, noise)
+            if self._external:
+                eng.nes_ext_update(self._ext_scores(eng, kw_score))
+            else:
+                eng.nes_run(k, noise)
             done, stopped = eng.nes_status()
             self.poll_times.append(time.time() - t_poll)
             if self.verbose:
@@ -160,6 +196,13 @@ class FakeBob(object):
     def get_grad(self, audio, fs=16000, bits_per_sample=16, n_jobs=10, debug=False):
         audio = self._column(audio)
         eng = self._nes_init(audio, 1)
+        if self._external:
+            eng.nes_ext_update(self._ext_scores(eng, dict(fs=fs, bits_per_sample=bits_per_sample, n_jobs=n_jobs, debug=debug)),
+                               gradient_only=True)
+            grad, losses, score0 = eng.nes_gest()
+            self.draws += 1
+            score = score0[0] if self.task == "SV" else score0
+            return float(np.mean(losses[1:])), grad[:, np.newaxis], np.array([losses[0]]), score
         noise = self._host_noise(audio.shape[0]) if self.rng == "numpy" else None
         final_loss, grad, adver_loss, score0 = eng.nes_get_grad(noise)
         self.draws += 1
@@ -202,7 +245,7 @@ class FakeBob(object):
         self.attack_type = UNTARGETED
         n = audio.shape[0]
         try:
-            if self.rng == "philox":
+            if self.rng == "philox" and not self._external:
                 return self._estimate_threshold_device(audio)
             eng = self._nes_init(audio, 1)
             iter_outer, n_iters, times = 0, 0, 0.
@@ -231,8 +274,12 @@ class FakeBob(object):
                         if self.verbose:
                             print("--- early stop at iter_inner:%d ---" % (iter_inner))
                         break
-                    noise = self._host_noise(n)
-                    loss, _, _, _ = eng.nes_get_grad(noise)
+                    if self._external:
+                        eng.nes_ext_update(self._ext_scores(eng, dict(fs=fs, bits_per_sample=bits_per_sample, n_jobs=n_jobs, debug=debug)),
+                                           gradient_only=True)
+                        loss = float(np.mean(eng.nes_gest()[1][1:]))
+                    else:
+                        loss, _, _, _ = eng.nes_get_grad(self._host_noise(n))
                     self.draws += 1
                     last_ls.append(loss)
                     last_ls = last_ls[-self.plateau_length:]

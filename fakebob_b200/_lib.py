@@ -28,7 +28,7 @@ class NesParams(C.Structure):
                 ("threshold", C.c_double), ("adver_thresh", C.c_double), ("epsilon", C.c_double),
                 ("sigma", C.c_double), ("max_lr", C.c_double), ("min_lr", C.c_double), ("momentum", C.c_double),
                 ("plateau_drop", C.c_double), ("seed", C.c_uint64), ("draw_base", C.c_uint64),
-                ("z_norm_means", C.POINTER(C.c_double)), ("z_norm_stds", C.POINTER(C.c_double))]
+                ("z_norm_means", C.POINTER(C.c_double)), ("z_norm_stds", C.POINTER(C.c_double)), ("external_scorer", C.c_int)]
 
 
 TASK = {"CSI": 0, "OSI": 1, "SV": 2}
@@ -73,6 +73,9 @@ _SIGS = {
     "fb_nes_read_grad": (C.c_int, [_P, _P, C.c_int64]),
     "fb_nes_estimate_begin": (C.c_int, [_P, C.c_double]),
     "fb_nes_continue": (C.c_int, [_P, C.c_double]),
+    "fb_nes_ext_perturb": (C.c_int, [_P, _P]),
+    "fb_nes_ext_update": (C.c_int, [_P, _P, C.c_int]),
+    "fb_nes_read_gest": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "fb_nes_get_grad": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P]),
     "fb_nes_apply_update": (C.c_int, [_P, C.c_double]),
     "fb_nes_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),

@@ -568,7 +568,7 @@ void fb_nes_destroy(fb_ctx *ctx) {
   FbNes *s = ctx->nes;
   if (!s) return;
   nes_drop_graph(s);
-  s->f64_pool.release(); s->noise64.release(); s->noise32.release(); s->flags.release(); s->dist_bits.release();
+  s->f64_pool.release(); s->noise64.release(); s->noise32.release(); s->flags.release(); s->dist_bits.release(); s->ext_scores.release();
   delete s;
   ctx->nes = nullptr;
 }
@@ -583,8 +583,13 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   FB_CHECK_ARG(p->plateau_length >= 1 && p->plateau_length <= 64, "plateau_length must be in [1,64]");
   FB_CHECK_ARG(p->max_iter >= 1, "max_iter must be >= 1");
   const int K = p->n_speakers;
-  const bool iv = ctx->arch == 1;
-  if (iv) {
+  const bool ext = p->external_scorer != 0;
+  const bool iv = !ext && ctx->arch == 1;
+  if (ext) {
+    int rk = 0, wd = 1;
+    fb_comm_info(ctx, &rk, &wd);
+    FB_CHECK_ARG(wd == 1, "black-box scorers run single-GPU");
+  } else if (iv) {
     FB_CHECK_ARG(ctx->iv && ctx->iv->K == K, "enrolled i-vectors do not match n_speakers");
     FB_CHECK_ARG(p->z_norm_means && p->z_norm_stds, "i-vector scorers need z-norm statistics");
   } else {
@@ -596,7 +601,7 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
     FB_CHECK_ARG(K >= 2, "this loss needs at least two speakers");
     FB_CHECK_ARG(p->label >= 0 && p->label < K, "label (true/target) out of range");
   }
-  if (p->task == FB_TASK_CSI) FB_CHECK_ARG(p->z_norm_means && p->z_norm_stds, "CSI needs z-norm statistics");
+  if (p->task == FB_TASK_CSI && !ext) FB_CHECK_ARG(p->z_norm_means && p->z_norm_stds, "CSI needs z-norm statistics");
   FB_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->nes) ctx->nes = new FbNes();
   FbNes *s = ctx->nes;
@@ -654,7 +659,7 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   d.dist_bits = s->dist_bits.p;
   d.N = n_samples; d.S = S; d.K = K; d.pairs_total = pairs_total; d.pairs_local = s->pairs_local; d.pair0 = p0;
   d.B_local = s->B_local; d.has_clean = s->has_clean ? 1 : 0;
-  d.znorm = (iv || p->task == FB_TASK_CSI) ? 1 : 0;
+  d.znorm = (ext || iv || p->task == FB_TASK_CSI) ? 1 : 0;      // black-box scores arrive final: (s - 0) / 1
   d.task = p->task; d.targeted = p->targeted; d.label = p->label; d.plateau_length = p->plateau_length;
   d.auto_stop = 1;
   d.kappa = p->adver_thresh; d.sigma = p->sigma; d.epsilon = p->epsilon; d.momentum = p->momentum;
@@ -663,7 +668,10 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   d.world = world; d.rank = rank;
   if ((rc = fb_comm_p2p_attach(ctx, &d, red_n))) return rc;
   FB_CUDA(cudaMemcpyAsync(d.audio, audio_host, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (d.znorm) {
+  std::vector<double> ext_one(K, 1.0);
+  if (ext) {
+    FB_CUDA(cudaMemcpyAsync(d.zstd, ext_one.data(), K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));   // zmean stays 0
+  } else if (d.znorm) {
     FB_CUDA(cudaMemcpyAsync(d.zmean, p->z_norm_means, K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(d.zstd, p->z_norm_stds, K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
@@ -677,10 +685,63 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
   // score() call) may have left the shared batch workspace laid out for another length or batch size.
   s->offsets.resize(s->B_local + 1);
   for (int b = 0; b <= s->B_local; ++b) s->offsets[b] = (int64_t)b * n_samples;
-  if ((rc = fb_prepare_tables(ctx))) return rc;
-  ctx->batch_tag = -1;
-  if ((rc = nes_claim_batch(ctx))) return rc;
+  if (ext) {
+    // no front-end / model workspace: the wave buffer for the batch and a score buffer [B][K]
+    if ((rc = ctx->wave.ensure((size_t)s->B_local * s->N + 8))) return rc;
+    if ((rc = s->ext_scores.ensure((size_t)s->B_local * K))) return rc;
+    ctx->batch_tag = -1;
+  } else {
+    if ((rc = fb_prepare_tables(ctx))) return rc;
+    ctx->batch_tag = -1;
+    if ((rc = nes_claim_batch(ctx))) return rc;
+  }
   FB_CUDA(cudaStreamSynchronize(ctx->stream));        // the host arrays (audio, z-norm, locals above) may go away now
+  return FB_OK;
+}
+
+extern "C" int fb_nes_ext_perturb(fb_ctx *ctx, int16_t *wave_host) {
+  FB_CHECK_ARG(ctx && ctx->nes && wave_host, "fb_nes_init has not been called");
+  FbNes *s = ctx->nes;
+  FB_CHECK_ARG(s->p.external_scorer, "the session was not created for an external scorer");
+  FB_CHECK_ARG(s->p.rng == FB_RNG_PHILOX, "external scorers use the device noise generator");
+  FB_CUDA(cudaSetDevice(ctx->device));
+  const FbNesDev d = s->dev;
+  dim3 gp(fb_div_up(fb_div_up(s->N, 4), 256), s->pairs_local < 8 ? s->pairs_local : 8);
+  FB_CUDA(fb_launch(perturb_kernel, gp, dim3(256), 0, ctx->stream, d, ctx->wave.p, s->N, 1));
+  ctx->launches += 1;
+  FB_CUDA(cudaMemcpyAsync(wave_host, ctx->wave.p, (size_t)s->B_local * s->N * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_nes_read_gest(fb_ctx *ctx, double *gest_host, int64_t n_samples, double *losses_host, double *score0_host) {
+  FB_CHECK_ARG(ctx && ctx->nes && n_samples == ctx->nes->N, "bad argument");
+  FbNes *s = ctx->nes;
+  if (gest_host) FB_CUDA(cudaMemcpyAsync(gest_host, s->dev.gest, n_samples * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (losses_host)
+    FB_CUDA(cudaMemcpyAsync(losses_host, s->dev.red + s->N, (size_t)(s->dev.S + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (score0_host)
+    FB_CUDA(cudaMemcpyAsync(score0_host, s->dev.red + s->N + s->dev.S + 1, (size_t)s->dev.K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_nes_ext_update(fb_ctx *ctx, const double *scores_host, int gradient_only) {
+  FB_CHECK_ARG(ctx && ctx->nes && scores_host, "fb_nes_init has not been called");
+  FbNes *s = ctx->nes;
+  FB_CHECK_ARG(s->p.external_scorer, "the session was not created for an external scorer");
+  FB_CUDA(cudaSetDevice(ctx->device));
+  const FbNesDev d = s->dev;
+  FB_CUDA(cudaMemcpyAsync(s->ext_scores.p, scores_host, (size_t)s->B_local * d.K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const int g = gradient_only ? 1 : 0;
+  FB_CUDA(fb_launch(nes_loss_kernel, dim3(1), dim3(256), 0, ctx->stream, d, (const double *)s->ext_scores.p, d.K, g ? 2 : 1));
+  if (d.S >= 8 && d.S <= 128)
+    FB_CUDA(fb_launch(nes_update8_kernel, dim3(fb_div_up(s->N, 128)), dim3(128), 0, ctx->stream, d, g ? 3 : 0));
+  else
+    FB_CUDA(fb_launch(nes_update_kernel, dim3(fb_div_up(s->N, 128)), dim3(128), 0, ctx->stream, d, g ? 3 : 0, 1, 0.0));
+  ctx->launches += 2;
+  if (!g) s->enqueued += 1;
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
   return FB_OK;
 }
 

@@ -51,6 +51,7 @@ struct FbNes {
   DevBuf<float> noise32;
   DevBuf<unsigned long long> flags;       // 8 x u64 holding 16 ints, then 16 u64 counters
   DevBuf<unsigned long long> dist_bits;
+  DevBuf<double> ext_scores;              // [B][K] scores handed in by a black-box scorer (fb_nes_ext_update)
   size_t red_count = 0;
   int enqueued = 0;
   cudaGraph_t graph = nullptr;

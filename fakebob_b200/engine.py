@@ -194,7 +194,7 @@ class GmmEngine:
     # ---- NES -------------------------------------------------------------------------------------
     def nes_init(self, audio, task, attack_type, n_speakers, label, threshold, adver_thresh, epsilon, max_iter,
                  max_lr, min_lr, samples_per_draw, sigma, momentum, plateau_length, plateau_drop,
-                 rng="philox", seed=0, draw_base=0, z_means=None, z_stds=None):
+                 rng="philox", seed=0, draw_base=0, z_means=None, z_stds=None, external=False):
         audio = np.ascontiguousarray(np.asarray(audio, dtype=np.float64).reshape(-1))
         p = _lib.NesParams()
         p.task = _lib.TASK[task]
@@ -208,6 +208,7 @@ class GmmEngine:
         p.threshold, p.adver_thresh, p.epsilon, p.sigma = threshold, adver_thresh, epsilon, sigma
         p.max_lr, p.min_lr, p.momentum, p.plateau_drop = max_lr, min_lr, momentum, plateau_drop
         p.seed, p.draw_base = seed, draw_base
+        p.external_scorer = 1 if external else 0
         keep = [audio]
         if z_means is not None:
             zm = np.ascontiguousarray(z_means, dtype=np.float64)
@@ -220,6 +221,25 @@ class GmmEngine:
         self._nes_N = audio.shape[0]
         self._nes_K = n_speakers
         self._nes_S2 = samples_per_draw // 2
+
+    # ---- black-box scorers: the device keeps the attack state, the caller scores the batch ------------------------------
+    def nes_ext_perturb(self):
+        """-> (S+1, N) int16: row 0 the current adversarial audio, then +noise rows, then -noise rows (FAKEBOB.py:234-237)."""
+        w = np.empty((2 * self._nes_S2 + 1, self._nes_N), dtype=np.int16)
+        _lib.check(self.lib.fb_nes_ext_perturb(self.h, _ptr(w)))
+        return w
+
+    def nes_ext_update(self, scores, gradient_only=False):
+        sc = np.ascontiguousarray(np.asarray(scores, dtype=np.float64).reshape(2 * self._nes_S2 + 1, self._nes_K))
+        _lib.check(self.lib.fb_nes_ext_update(self.h, _ptr(sc), 1 if gradient_only else 0))
+
+    def nes_gest(self):
+        """-> (gradient estimate (N,), losses (S+1,), clean scores (K,)) of the last gradient-only step."""
+        g = np.empty(self._nes_N, dtype=np.float64)
+        ls = np.empty(2 * self._nes_S2 + 1, dtype=np.float64)
+        sc = np.empty(self._nes_K, dtype=np.float64)
+        _lib.check(self.lib.fb_nes_read_gest(self.h, _ptr(g), g.shape[0], _ptr(ls), _ptr(sc)))
+        return g, ls, sc
 
     def nes_run(self, n_iters, noise=None):
         """noise (host rng): (n_iters, S/2, N) float64, pair-major."""
@@ -331,6 +351,21 @@ class GmmEngine:
             self.p2p = all(flags)
             if not self.p2p:
                 os.environ["FB_NO_P2P"] = "1"          # every rank must take the same path
+
+
+class ExternalEngine(GmmEngine):
+    """A bare context for attacking a black-box scorer (reference README.md:136): no resident models; the NES state, noise
+    generator, quantisation, gradient and update run on the device, the caller scores each batch."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        self.device = default_device() if device is None else device
+        h = C.c_void_p()
+        _lib.check(self.lib.fb_ctx_create(self.device, C.byref(h)))
+        self.h = h
+        self.n_models = 0
+        self._nes_keep = None
+        self._last_B = 0
 
 
 class IvectorEngine(GmmEngine):

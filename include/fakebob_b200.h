@@ -165,6 +165,8 @@ typedef struct fb_nes_params {
   uint64_t draw_base;        /* Philox iteration counter of the first draw */
   const double *z_norm_means;/* CSI only, host, K */
   const double *z_norm_stds; /* CSI only, host, K */
+  int    external_scorer;    /* 1 = black-box model (README.md:136: any object with score()/make_decisions()): the context needs
+                                no resident models; iterate with fb_nes_ext_perturb / fb_nes_ext_update */
 } fb_nes_params;
 
 /* Creates device state for one utterance of n_samples (float64 audio in [-1,1], host). */
@@ -181,6 +183,8 @@ int fb_nes_status(fb_ctx *ctx, int *iters_done, int *stopped);
 int fb_nes_read_log(fb_ctx *ctx, double *rows_host, int max_rows);
 int fb_nes_read_adver(fb_ctx *ctx, double *adver_host, int64_t n_samples);
 int fb_nes_read_grad(fb_ctx *ctx, double *grad_host, int64_t n_samples);
+/* The last gradient estimate (before momentum) and the losses [S+1] / clean scores [K] it was computed from. */
+int fb_nes_read_gest(fb_ctx *ctx, double *gest_host, int64_t n_samples, double *losses_host, double *score0_host);
 /* FakeBob.estimate_threshold on the device (FAKEBOB.py:76-137).  The reference scores the current adversarial audio with
  * make_decisions() and then, separately, the S+1 batch of get_grad(); column 0 of that batch IS the current audio, so one
  * batch per inner iteration serves both.  After fb_nes_init (untargeted OSI / SV, max_iter = an upper bound on the total
@@ -190,6 +194,15 @@ int fb_nes_read_grad(fb_ctx *ctx, double *grad_host, int64_t n_samples);
  * The stopping iteration applies no update and does not consume its noise draw, like the reference's break / return. */
 int fb_nes_estimate_begin(fb_ctx *ctx, double accept_threshold);
 int fb_nes_continue(fb_ctx *ctx, double threshold);
+/* Black-box scorers (fb_nes_params.external_scorer = 1): the device keeps the attack state, draws the noise, quantises and
+ * applies the update; the S+1 audios of an iteration go to the host, the caller scores them with its own system and hands
+ * the scores back.  fb_nes_ext_perturb writes the batch as int16 PCM [S+1][n_samples] (row 0 = the current adversarial audio,
+ * rows 1..S/2 = +noise, the rest = -noise: the column order of FAKEBOB.py:234-237).  fb_nes_ext_update takes the scores
+ * [S+1][K] (K = n_speakers; SV: K = 1) exactly as score() returned them, computes the losses, the gradient estimate and the
+ * update (FAKEBOB.py:239-246,181-203); gradient_only = 1 stops after the estimate (FakeBob.get_grad; read it with
+ * fb_nes_read_gest, apply it with fb_nes_apply_update).  Stop state / log as with fb_nes_status / fb_nes_read_log. */
+int fb_nes_ext_perturb(fb_ctx *ctx, int16_t *wave_host);
+int fb_nes_ext_update(fb_ctx *ctx, const double *scores_host, int gradient_only);
 /* One gradient estimate without the update: FakeBob.get_grad (FAKEBOB.py:223-246). */
 int fb_nes_get_grad(fb_ctx *ctx, const double *noise_host, double *final_loss, double *adver_loss,
                     double *score0_host, double *grad_host);

@@ -208,7 +208,61 @@ def test_estimate_threshold_on_device_matches_oracle_search(scorers, task, capsy
     assert abs(fb.threshold - ob.threshold) < 5e-4 and fb.draws == ob.draws
 
 
-def test_requires_device_backed_model():
+class _BlackBox(object):
+    """A foreign system in the sense of the reference's README.md:136: only score() / make_decisions(), nothing else."""
+
+    def __init__(self, inner):
+        self._inner = inner
+        self.threshold = inner.threshold
+        self.calls = 0
+
+    def score(self, audios, fs=16000, bits_per_sample=16, n_jobs=5, debug=False):
+        self.calls += 1
+        return self._inner.score(audios, fs=fs, bits_per_sample=bits_per_sample)
+
+    def make_decisions(self, audios, fs=16000, bits_per_sample=16, n_jobs=5, debug=False):
+        self._inner.threshold = self.threshold
+        return self._inner.make_decisions(audios, fs=fs, bits_per_sample=bits_per_sample)
+
+
+@pytest.mark.parametrize("task,attack_type,kw", [("OSI", "targeted", dict(threshold=0.05, target=2)), ("SV", "untargeted", dict(threshold=1.0)),
+                                                 ("CSI", "untargeted", dict(true=0))])
+def test_black_box_model_attack_equals_resident_model_attack(scorers, task, attack_type, kw):
+    """FakeBob on a duck-typed scorer: NES state, noise, quantisation, loss, gradient and update on the device, scoring by
+    the caller's score().  Wrapping one of this package's scorers as a black box must reproduce the all-device attack."""
+    from fakebob_b200.FAKEBOB import FakeBob
+    inner = scorers[task]
+    box = _BlackBox(inner)
+    assert not hasattr(box, "_engine")
+    audio = make_audio(45, 1, n=16000)
+    hp = dict(max_iter=5, samples_per_draw=8, plateau_length=3)
+    fa = FakeBob(task, attack_type, inner, seed=31, verbose=False, **hp)
+    adv_a, flag_a = fa.attack(audio.copy(), None, **kw)
+    fb = FakeBob(task, attack_type, box, seed=31, verbose=False, **hp)
+    adv_b, flag_b = fb.attack(audio.copy(), None, **kw)
+    assert flag_a == flag_b and fa.iters_done == fb.iters_done and box.calls >= fb.iters_done
+    assert np.array_equal(adv_a, adv_b)
+    assert np.allclose(fa.log[:, :3], fb.log[:, :3], rtol=0, atol=1e-12)
+    # get_grad through the black box
+    fl, g, al, sc = fb.get_grad(audio)
+    assert g.shape == (16000, 1) and np.isfinite(g).all() and np.isfinite(fl)
+
+
+def test_black_box_estimate_threshold(scorers):
+    from fakebob_b200.FAKEBOB import FakeBob
+    inner = scorers["SV"]
+    audio = make_audio(46, 2, n=16000)
+    box = _BlackBox(inner)
+    box.threshold = float(inner.score(audio)) + 0.02
+    try:
+        fb = FakeBob("SV", "targeted", box, samples_per_draw=8, seed=77, verbose=False, max_lr=0.001)
+        score, n_iters, secs = fb.estimate_threshold(audio)
+    finally:
+        inner.threshold = 0.0
+    assert score >= box.threshold and n_iters >= 1 and fb.attack_type == "targeted"
+
+
+def test_model_must_have_the_scorer_interface():
     from fakebob_b200.FAKEBOB import FakeBob
 
     class Stub:
@@ -216,4 +270,4 @@ def test_requires_device_backed_model():
             return 0.0
 
     with pytest.raises(TypeError):
-        FakeBob("SV", "untargeted", Stub())
+        FakeBob("SV", "untargeted", Stub())                         # no make_decisions()

@@ -143,7 +143,16 @@ def test_fails_loudly_without_gpu_or_device_model():
         def score(self, a):
             return 0.0
     with pytest.raises(TypeError):
-        FakeBob("SV", "untargeted", Stub())
+        FakeBob("SV", "untargeted", Stub())                     # not a scorer: no make_decisions()
+
+    class BlackBox(Stub):
+        def make_decisions(self, a):
+            return -1, 0.0
+    if not torch.cuda.is_available():
+        # a black-box model is accepted, but its attack still needs the device (NES state, noise, update): no CPU fallback
+        fb = FakeBob("SV", "untargeted", BlackBox(), max_iter=1, samples_per_draw=2, verbose=False)
+        with pytest.raises(_lib.FakebobLibraryError):
+            fb.attack(np.zeros(1600), None, threshold=1.0)
 
 
 def test_synthetic_tree_layout(small_tree):
