@@ -18,7 +18,10 @@ void fb_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 bool fb_pdl_enabled() {
-  static const bool on = getenv("FB_NO_PDL") == nullptr;
+  // Measured on B200 inside the captured iteration graph (gpurun session s10): 229.1 vs 230.0 us / iteration at S = 50
+  // (no difference), 91.3 vs 80.1 us at S = 6 (programmatic edges are SLOWER when every kernel is launch-bound).
+  // Off unless FB_PDL=1.
+  static const bool on = getenv("FB_PDL") != nullptr && getenv("FB_NO_PDL") == nullptr;
   return on;
 }
 uint64_t fb_alloc_epoch() { return g_epoch.load(); }

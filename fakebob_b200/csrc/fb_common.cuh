@@ -209,10 +209,12 @@ struct FbNvtxSeq {
 };
 
 // ---- programmatic dependent launch ---------------------------------------------------------------------------------
-// Every kernel of the scoring / NES sequence is launched with the programmatic-stream-serialization attribute and starts
-// with FB_GRID_DEP_SYNC(): the next kernel's CTAs are scheduled (launch latency, prologue) while the previous kernel
-// drains, and block at griddepcontrol.wait until it has completed and flushed its memory.  The wait is executed
-// unconditionally, before any early return, so completion stays transitive along the chain.  FB_NO_PDL=1 launches plainly.
+// With FB_PDL=1 every kernel of the scoring / NES sequence is launched with the programmatic-stream-serialization attribute;
+// all of them start with FB_GRID_DEP_SYNC(): the next kernel's CTAs are scheduled (launch latency, prologue) while the
+// previous kernel drains, and block at griddepcontrol.wait until it has completed and flushed its memory.  The wait is
+// executed unconditionally, before any early return, so completion stays transitive along the chain.  Measured inside the
+// captured iteration graph it does not pay (equal at S = 50, 14 % slower at S = 6), so it is opt-in; without the attribute
+// griddepcontrol.wait is a no-op.
 bool fb_pdl_enabled();
 #ifdef __CUDACC__
 #define FB_GRID_DEP_SYNC()                                          \

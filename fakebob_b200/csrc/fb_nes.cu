@@ -689,6 +689,7 @@ extern "C" int fb_nes_init(fb_ctx *ctx, const fb_nes_params *p, const double *au
     // no front-end / model workspace: the wave buffer for the batch and a score buffer [B][K]
     if ((rc = ctx->wave.ensure((size_t)s->B_local * s->N + 8))) return rc;
     if ((rc = s->ext_scores.ensure((size_t)s->B_local * K))) return rc;
+    if ((rc = ctx->misc.ensure(8, true))) return rc;          // status word read by fb_nes_status
     ctx->batch_tag = -1;
   } else {
     if ((rc = fb_prepare_tables(ctx))) return rc;

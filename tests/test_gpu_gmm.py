@@ -209,3 +209,33 @@ def test_cuda_path_matches_committed_stage_fixture():
     assert half["means_invvars"].shape == g["spk_means_invvars"].shape and np.isfinite(half["gconsts"]).all()
     one.close()
     eng.close()
+
+
+def test_evaluation_helpers_on_device_scorers_match_oracle_scorers(small_tree, small_oracle_models):
+    """the numbers the reference's test.py prints (EER threshold search test.py:46-71, FRR / FAR / IER,
+    closed-set accuracy) from the device scorers equal those from the oracle scorers on the same ragged audio lists."""
+    from fakebob_b200 import evaluate as ev
+    from fakebob_b200.gmm_ubm_CSI import gmm_CSI
+    from fakebob_b200.gmm_ubm_OSI import gmm_OSI
+    from fakebob_b200.gmm_ubm_SV import gmm_SV
+    from oracle.scorers import OracleGmmCSI, OracleGmmOSI, OracleGmmSV
+    ubm, spk = small_oracle_models
+    models = small_tree["models"]
+    pre = small_tree["pre_model_dir"]
+    enrolled = [make_audio(9000 + k, k, n=(32000, 24000, 40000)[k]) for k in range(3)] + [make_audio(9100 + k, k) for k in range(3)]
+    labels = [0, 1, 2, 0, 1, 2]
+    illegal = [make_audio(700 + i, 9 + i, n=28000 + 1000 * i) for i in range(5)]
+    dev = gmm_OSI(small_tree["root"] + "/ev-osi", models, small_tree["ubm"], pre_model_dir=pre)
+    ref = OracleGmmOSI(ubm, spk)
+    r_dev, r_ref = ev.osi_error_rates(dev, enrolled, labels, illegal), ev.osi_error_rates(ref, enrolled, labels, illegal)
+    assert abs(r_dev["threshold"] - r_ref["threshold"]) < TOL_SCORE
+    assert (r_dev["frr"], r_dev["ier"], r_dev["far"]) == (r_ref["frr"], r_ref["ier"], r_ref["far"])
+    assert abs(dev.threshold - r_dev["threshold"]) < 1e-12            # stored on the model like test.py does
+    sv_d = gmm_SV(small_tree["root"] + "/ev-sv", models[0], small_tree["ubm"], pre_model_dir=pre)
+    sv_r = OracleGmmSV(ubm, spk[0])
+    own = [enrolled[0], enrolled[3]]
+    s_dev, s_ref = ev.sv_error_rates(sv_d, own, illegal), ev.sv_error_rates(sv_r, own, illegal)
+    assert abs(s_dev["threshold"] - s_ref["threshold"]) < TOL_SCORE and (s_dev["frr"], s_dev["far"]) == (s_ref["frr"], s_ref["far"])
+    csi_d = gmm_CSI(small_tree["root"] + "/ev-csi", models, pre_model_dir=pre)
+    csi_r = OracleGmmCSI(spk, [m[3] for m in models], [m[4] for m in models])
+    assert ev.csi_accuracy(csi_d, enrolled, labels) == ev.csi_accuracy(csi_r, enrolled, labels)

@@ -213,7 +213,7 @@ class _BlackBox(object):
 
     def __init__(self, inner):
         self._inner = inner
-        self.threshold = inner.threshold
+        self.threshold = getattr(inner, "threshold", 0.0)
         self.calls = 0
 
     def score(self, audios, fs=16000, bits_per_sample=16, n_jobs=5, debug=False):
