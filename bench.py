@@ -222,7 +222,7 @@ def load_reference_fakebob():
 
 
 def oracle_model(name, tree, iv_root=None):
-    from fakebob_b200 import kaldi_io
+    from oracle import kaldi_files as kaldi_io           # the oracle's own model reader
     from oracle.diag_gmm import DiagGmm
     from oracle.scorers import OracleGmmCSI, OracleGmmOSI, OracleIvOSI, OracleIvSV
     c = CONFIGS[name]

@@ -309,7 +309,9 @@ extern "C" int fb_debug_gmm_stats(long long *out_host) {
 #ifndef GMM_PARK_ISSUER_NS
 #define GMM_PARK_ISSUER_NS 400
 #endif
-template <bool kStore, bool kShared>
+// kNM > 0: the number of slots is known at compile time (shared mode), so the epilogue's per-slot running (max, sum) live in
+// registers and the slot loop is unrolled; kNM = 0: run-time slot count, the state sits in local memory.
+template <bool kStore, bool kShared, int kNM = 0>
 __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
 #ifdef GMM_STATS
   unsigned long long gt_entry;
@@ -564,7 +566,8 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     const int half = (warp - GMM_EPI_WARP0) >> 3;
     uint32_t job = tile;                               // this tile's jobs are tile, tile + 2, tile + 4, ...
     const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kTmemAcc + half * NC;
-    float mm[kShared ? FB_MAX_MODELS : 1], ss[kShared ? FB_MAX_MODELS : 1];
+    constexpr int kState = kShared ? (kNM > 0 ? kNM : FB_MAX_MODELS) : 1;
+    float mm[kState], ss[kState];
     int run_item = -1;                                  // the running maxima belong to this (super[, model])
     STAT_DECL(st_epi_full);
 #ifdef GMM_STATS
@@ -592,13 +595,19 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
     // The running (max, sum) of a row is kept over the whole run of consecutive stages this CTA computes for the same
     // (rows[, model]) -- a "segment" -- so the cutoff is relative to the running maximum; one partial per segment and column
     // range, stored at the index of the segment's first stage.
-    const int n_run = kShared ? g.n_models : 1;
+    const int n_run = kShared ? (kNM > 0 ? kNM : g.n_models) : 1;
     int seg_start = 0, seg_row = 0, seg_model = 0;
     auto flush = [&]() {
       if constexpr (!kStore) {
-        for (int r = 0; r < n_run; ++r) {
-          const int mdl = kShared ? r : seg_model;
-          g.part[(((size_t)mdl * nst + seg_start) * FB_GMM_EPI_HALVES + half) * g.rows_cap + seg_row] = make_float2(mm[r], ss[r]);
+        if constexpr (kNM > 0) {
+#pragma unroll
+          for (int r = 0; r < kNM; ++r)
+            g.part[(((size_t)r * nst + seg_start) * FB_GMM_EPI_HALVES + half) * g.rows_cap + seg_row] = make_float2(mm[r], ss[r]);
+        } else {
+          for (int r = 0; r < n_run; ++r) {
+            const int mdl = kShared ? r : seg_model;
+            g.part[(((size_t)mdl * nst + seg_start) * FB_GMM_EPI_HALVES + half) * g.rows_cap + seg_row] = make_float2(mm[r], ss[r]);
+          }
         }
       }
     };
@@ -610,7 +619,12 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
       const int row = sp * (2 * FB_TILE_M) + tile * FB_TILE_M + quad * 32 + lane;
       if (item != run_item) {
         if (run_item >= 0) flush();
-        for (int i = 0; i < n_run; ++i) { mm[i] = -INFINITY; ss[i] = 0.f; }
+        if constexpr (kNM > 0) {
+#pragma unroll
+          for (int i = 0; i < kNM; ++i) { mm[i] = -INFINITY; ss[i] = 0.f; }
+        } else {
+          for (int i = 0; i < n_run; ++i) { mm[i] = -INFINITY; ss[i] = 0.f; }
+        }
         run_item = item;
         seg_start = stage; seg_row = row; seg_model = model;
       }
@@ -627,8 +641,7 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
           mm[0] = m;
           ss[0] = sacc;
         }
-#pragma unroll 1
-        for (int r = 1; r < g.n_models; ++r) {
+        auto slot_job = [&](float &m_r, float &s_r) {
           float v[NC];
           fetch(v);
 #pragma unroll
@@ -636,14 +649,21 @@ __global__ void __launch_bounds__(GMM_THREADS, 1) gmm_umma_kernel(GmmArgs g) {
             const float2 t = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(q[i], q[i + 1]));
             v[i] = t.x; v[i + 1] = t.y;
           }
-          float m = mm[r], sacc = ss[r];
+          float m = m_r, sacc = s_r;
 #ifndef GMM_NO_LSE
           lse_stage<NC>(v, m, sacc);
 #else
           m = fmaxf(m, v[0] + v[NC - 1]);
 #endif
-          mm[r] = m;
-          ss[r] = sacc;
+          m_r = m;
+          s_r = sacc;
+        };
+        if constexpr (kNM > 0) {
+#pragma unroll
+          for (int r = 1; r < kNM; ++r) slot_job(mm[r], ss[r]);
+        } else {
+#pragma unroll 1
+          for (int r = 1; r < g.n_models; ++r) slot_job(mm[r], ss[r]);
         }
       } else {
         float v[NC];
@@ -925,6 +945,9 @@ extern "C" int fb_finalize_gmms(fb_ctx *ctx, int n_models) {
   if (fb_once_per_device(attr_set_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
     FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
+    FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<false, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
     FB_CUDA(cudaFuncSetAttribute(gmm_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLaunch));
   }
   return FB_OK;
@@ -953,8 +976,18 @@ int fb_run_gmm_flag(fb_ctx *ctx, const int *done_flag) {
     if (max_units < grid) grid = (int)max_units;
     umma_grid = grid;
     a.ll_out = nullptr;
-    if (ctx->gmm_shared) FB_CUDA(fb_launch(gmm_umma_kernel<false, true>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
-    else FB_CUDA(fb_launch(gmm_umma_kernel<false, false>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
+    if (ctx->gmm_shared) {
+      // the slot counts of the reference's configurations get register-resident epilogue state: SV (UBM + 1), CSI with
+      // the default 5 speakers, OSI (UBM + 5); any other count takes the general instantiation
+      static const bool generic_only = getenv("FB_GMM_GENERIC_SLOTS") != nullptr;
+      const int nm = generic_only ? 0 : ctx->n_models;
+      if (nm == 6) FB_CUDA(fb_launch(gmm_umma_kernel<false, true, 6>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
+      else if (nm == 5) FB_CUDA(fb_launch(gmm_umma_kernel<false, true, 5>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
+      else if (nm == 2) FB_CUDA(fb_launch(gmm_umma_kernel<false, true, 2>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
+      else FB_CUDA(fb_launch(gmm_umma_kernel<false, true>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
+    } else {
+      FB_CUDA(fb_launch(gmm_umma_kernel<false, false>, dim3(grid), dim3(GMM_THREADS), kSmemLaunch, ctx->stream, a));
+    }
   }
   fb_prof_mark(ctx, 4);
   nv.next("fb:gmm_frame_reduce");

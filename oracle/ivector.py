@@ -198,9 +198,9 @@ class IvectorSystem:
 
 
 def load_system(pre_model_dir, cfg=None):
-    """Build the oracle system from a Kaldi-format pre-models/ tree (uses the product's file reader for parsing only)."""
+    """Build the oracle system from a Kaldi-format pre-models/ tree, parsed with the oracle's own reader (oracle/kaldi_files.py)."""
     import os
-    from fakebob_b200 import kaldi_io
+    from . import kaldi_files as kaldi_io
     fg = kaldi_io.read_full_gmm(os.path.join(pre_model_dir, "final.ubm"))
     ie = kaldi_io.read_ivector_extractor(os.path.join(pre_model_dir, "final.ie"))
     pl = kaldi_io.read_plda(os.path.join(pre_model_dir, "plda"))

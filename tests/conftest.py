@@ -31,9 +31,9 @@ def pytest_collection_modifyitems(config, items):
 
 
 def load_oracle_gmm(path):
-    from fakebob_b200 import kaldi_io
+    from oracle import kaldi_files      # the oracle's own file reader, not the product's
     from oracle.diag_gmm import DiagGmm
-    g = kaldi_io.read_diag_gmm(path)
+    g = kaldi_files.read_diag_gmm(path)
     return DiagGmm(g["weights"], g["means_invvars"], g["inv_vars"], g["gconsts"])
 
 

@@ -34,7 +34,8 @@ from oracle.diag_gmm import DiagGmm  # noqa: E402
 
 
 def load_gmm(path):
-    g = kaldi_io.read_diag_gmm(path)
+    from oracle import kaldi_files
+    g = kaldi_files.read_diag_gmm(path)
     return DiagGmm(g["weights"], g["means_invvars"], g["inv_vars"], g["gconsts"])
 
 

@@ -32,11 +32,13 @@ def main():
     w = r.dirichlet(np.full(C, 5.0))
     ubm = DiagGmm.from_moments(w, mu, var)
     spk = ubm.map_adapt_means(voiced[::2], tau=10.0)
+    spk_all = ubm.map_adapt_means(voiced, tau=10.0)      # what enrolling this very utterance gives (fb_map_adapt_host)
     out = os.path.join(HERE, "kaldi_stages.npz")
     np.savez_compressed(
         out, wave=wave, mfcc=mfcc.astype(np.float32), vad=vad.astype(np.int8), voiced_feats=voiced.astype(np.float32),
         ubm_weights=ubm.weights, ubm_means_invvars=ubm.means_invvars, ubm_inv_vars=ubm.inv_vars, ubm_gconsts=ubm.gconsts,
         spk_means_invvars=spk.means_invvars, spk_gconsts=spk.gconsts,
+        spk_all_means_invvars=spk_all.means_invvars, spk_all_gconsts=spk_all.gconsts, spk_all_occupancy=spk_all.occupancy,
         frame_ll_ubm=ubm.frame_loglikes(voiced), frame_ll_spk=spk.frame_loglikes(voiced),
         avg_ll=np.array([float(ubm.avg_loglike(voiced)), float(spk.avg_loglike(voiced))]))
     print(out, "frames", mfcc.shape[0], "voiced", voiced.shape[0], "avg ll", float(ubm.avg_loglike(voiced)), float(spk.avg_loglike(voiced)))

@@ -413,3 +413,24 @@ def test_library_contains_sm100a_tensor_core_and_tma_code():
                           capture_output=True, text=True, timeout=300).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTCCP", "UBLKCP", "SYNCS.PHASECHK"):
         assert mnemonic in sass, mnemonic
+
+
+def test_product_and_oracle_model_readers_agree(small_iv_tree):
+    """The product's Kaldi file reader (fakebob_b200/kaldi_io.py) and the oracle's independent one (oracle/kaldi_files.py)
+    parse every model file of the synthetic tree to the same arrays."""
+    from oracle import kaldi_files as okf
+    t = small_iv_tree
+    pre = t["pre_model_dir"]
+    a, b = kaldi_io.read_diag_gmm(t["ubm"]), okf.read_diag_gmm(t["ubm"])
+    for k in ("weights", "gconsts", "means_invvars", "inv_vars"):
+        assert np.array_equal(np.asarray(a[k]), b[k])
+    a, b = kaldi_io.read_full_gmm(os.path.join(pre, "final.ubm")), okf.read_full_gmm(os.path.join(pre, "final.ubm"))
+    for k in ("weights", "gconsts", "means_invcovars", "inv_covars"):
+        assert np.array_equal(np.asarray(a[k]), b[k])
+    a, b = kaldi_io.read_ivector_extractor(os.path.join(pre, "final.ie")), okf.read_ivector_extractor(os.path.join(pre, "final.ie"))
+    assert np.array_equal(a["M"], b["M"]) and np.array_equal(a["sigma_inv"], b["sigma_inv"]) and a["prior_offset"] == b["prior_offset"]
+    a, b = kaldi_io.read_plda(os.path.join(pre, "plda")), okf.read_plda(os.path.join(pre, "plda"))
+    for k in ("mean", "transform", "psi"):
+        assert np.array_equal(np.asarray(a[k]), b[k])
+    assert np.array_equal(np.asarray(kaldi_io.read_vector(os.path.join(pre, "mean.vec"))), okf.read_vector(os.path.join(pre, "mean.vec")))
+    assert np.array_equal(np.asarray(kaldi_io.read_matrix(os.path.join(pre, "transform.mat"))), okf.read_matrix(os.path.join(pre, "transform.mat")))

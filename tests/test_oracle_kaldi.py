@@ -121,6 +121,8 @@ def test_oracle_reproduces_committed_stage_fixture():
     assert abs(float(ubm.avg_loglike(X)) - g["avg_ll"][0]) < 1e-4 and abs(float(spk.avg_loglike(X)) - g["avg_ll"][1]) < 1e-4
     re = ubm.map_adapt_means(X[::2], tau=10.0)
     assert np.abs(re.means_invvars - g["spk_means_invvars"]).max() < 2e-4 and np.abs(re.gconsts - g["spk_gconsts"]).max() < 2e-4
+    re = ubm.map_adapt_means(X, tau=10.0)
+    assert np.abs(re.means_invvars - g["spk_all_means_invvars"]).max() < 2e-4 and np.abs(re.occupancy - g["spk_all_occupancy"]).max() < 1e-3
 
 
 def test_oracle_reproduces_committed_fullsize_fixture(tmp_path):
@@ -131,7 +133,7 @@ def test_oracle_reproduces_committed_fullsize_fixture(tmp_path):
     import fullsize_util as fu
     from oracle import kaldi_feats as kf
     from oracle.diag_gmm import DiagGmm
-    from fakebob_b200 import kaldi_io
+    from oracle import kaldi_files
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_c2.npz"))
     tree = fu.build_c2_tree(str(tmp_path))
     assert fu.checksums_close(fu.gmm_checksums(tree), g["checksums"], rtol=1e-5)
@@ -139,7 +141,7 @@ def test_oracle_reproduces_committed_fullsize_fixture(tmp_path):
     X = kf.voiced_features(g["wave0"])
     assert X.shape == g["feats0"].shape and np.abs(X - g["feats0"]).max() < 2e-4
     for k, path in enumerate([tree["ubm"]] + [m[2] for m in tree["models"]]):
-        p = kaldi_io.read_diag_gmm(path)
+        p = kaldi_files.read_diag_gmm(path)
         gm = DiagGmm(p["weights"], p["means_invvars"], p["inv_vars"], p["gconsts"])
         assert np.abs(gm.frame_loglikes(X) - g["frame_ll0"][k]).max() < 5e-4
         assert abs(float(gm.avg_loglike(X)) - g["avg_ll0"][k]) < 1e-4
