@@ -15,6 +15,7 @@
 // The derived extractor matrices (Sigma^-1 M, U) are computed ONCE at load on the device (Kaldi recomputes them on every
 // ivector-extract invocation).
 #include "fb_common.cuh"
+#include "fb_tma.cuh"
 #include <cooperative_groups.h>
 #include "fb_ivector.cuh"
 #include <math.h>
@@ -205,28 +206,38 @@ fgmm_post_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, 
 // ------------------------------------------------------------------------------------------------
 #define IV_GROUP 8
 #define IV_PACKED_PAD ((IV_PACKED + 3) & ~3)
-#define IV_XX_REGS ((IV_PACKED + 31) / 32)          // 83
+#define IV_ENT (IV_PACKED + FB_DIM)                 // a staged component: packed inverse covariance, then mean x inverse covariance
+#define IV_XX_PAIRS ((IV_ENT + 63) / 64)            // 43 register pairs per lane
+static_assert(IV_PACKED % 2 == 0 && IV_ENT % 2 == 0, "pairs of entries");
 #define IV_POST_STAGES 4                            // covariance blocks in flight: an L2 round trip (~1 us) per 0.3 us of compute
-static_assert(IV_PACKED % 4 == 0 && FB_DIM % 4 == 0, "16-byte cp.async needs 16-byte aligned component blocks");
+static_assert(IV_PACKED % 4 == 0 && FB_DIM % 4 == 0, "bulk copies need 16-byte aligned component blocks of 16 n bytes");
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, const float *__restrict__ gconsts,
                        const float *__restrict__ means_invcovars, const float *__restrict__ inv_covars_packed,
                        const unsigned short *__restrict__ rc_table, const int *__restrict__ frame_off,
                        const int *__restrict__ vrank, const int *__restrict__ row_off, int B, int C, int n_chunks,
                        float min_post, float *__restrict__ post, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  __shared__ __align__(16) float s_S[IV_POST_STAGES][IV_PACKED_PAD];
-  __shared__ __align__(16) float s_mic[IV_POST_STAGES][FB_DIM];
+  __shared__ __align__(16) float s_S[IV_POST_STAGES][IV_ENT];
+  __shared__ float s_gc[IV_GROUP * IV_NSEL];
   __shared__ float s_x[IV_GROUP][FB_DIM];
   __shared__ unsigned s_bitmap[128];                  // C <= 4096
   __shared__ int s_list[IV_GROUP * IV_NSEL];
   __shared__ int s_n;
+  __shared__ __align__(8) uint64_t s_bar[2 * IV_POST_STAGES];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x / n_chunks, chunk = blockIdx.x - t * n_chunks;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < IV_POST_STAGES; ++k) {
+      tma_bar_init(tma_smem_u32(s_bar + k), 1);
+      tma_bar_init(tma_smem_u32(s_bar + IV_POST_STAGES + k), IV_GROUP);      // one arrival per consumer warp
+    }
+    tma_bar_init_fence();
+  }
   // row of this warp: audio chunk * 8 + w at frame index t, -1 = not voiced / beyond the utterance
   int row = -1;
-  {
+  if (w < IV_GROUP) {
     const int b = chunk * IV_GROUP + w;
     if (b < B) {
       const int f0 = frame_off[b];
@@ -238,20 +249,26 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
   }
   if (threadIdx.x < 128) s_bitmap[threadIdx.x] = 0u;
   const int sel = (row >= 0 && lane < IV_NSEL) ? gsel[(size_t)row * IV_NSEL + lane] : -1;
-  for (int d = lane; d < FB_DIM; d += 32) s_x[w][d] = (row >= 0) ? feats[(size_t)row * FB_DIM + d] : 0.f;
+  if (w < IV_GROUP)
+    for (int d = lane; d < FB_DIM; d += 32) s_x[w][d] = (row >= 0) ? feats[(size_t)row * FB_DIM + d] : 0.f;
   __syncthreads();
   if (sel >= 0) atomicOr(&s_bitmap[sel >> 5], 1u << (sel & 31));
-  // this row's products, in the lane's registers: entry e = lane + 32 m
-  float xx[IV_XX_REGS];
+  // this row's multipliers, in the lane's registers as PAIRS: entries e = 2 lane + 64 m and e + 1, so a component costs one
+  // 64-bit shared-memory load and one packed FFMA2 per two entries.  Entry e < IV_PACKED: x_r x_c (halved on the diagonal)
+  // against the packed inverse covariance; entry IV_PACKED + d: -x_d against mean x inverse covariance, so that one pass
+  // over the staged block yields q - lin
+  float2 xx[IV_XX_PAIRS];
 #pragma unroll
-  for (int m = 0; m < IV_XX_REGS; ++m) {
-    const int e = lane + 32 * m;
-    float v = 0.f;
-    if (e < IV_PACKED) {
-      const unsigned short rc = rc_table[e];
-      const int rr = rc >> 8, cc = rc & 255;
-      const float p = s_x[w][rr] * s_x[w][cc];
-      v = (rr == cc) ? 0.5f * p : p;
+  for (int m = 0; m < IV_XX_PAIRS; ++m) {
+    const int e = 2 * lane + 64 * m;
+    float2 v = make_float2(0.f, 0.f);
+    if (e < IV_PACKED) {                              // IV_PACKED is even: a pair is on one side as a whole
+      const unsigned short rc0 = rc_table[e], rc1 = rc_table[e + 1];
+      const int r0 = rc0 >> 8, c0 = rc0 & 255, r1 = rc1 >> 8, c1 = rc1 & 255;
+      const float p0 = s_x[w][r0] * s_x[w][c0], p1 = s_x[w][r1] * s_x[w][c1];
+      v = make_float2((r0 == c0) ? 0.5f * p0 : p0, (r1 == c1) ? 0.5f * p1 : p1);
+    } else if (e < IV_ENT) {
+      v = make_float2(-s_x[w][e - IV_PACKED], -s_x[w][e + 1 - IV_PACKED]);
     }
     xx[m] = v;
   }
@@ -284,46 +301,54 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
   __syncthreads();
   const int n_union = s_n;
   if (n_union == 0) return;
-  auto stage = [&](int ui) {                          // cp.async of component s_list[ui] into buffer ui % IV_POST_STAGES
-    if (ui < n_union) {
-      const int c = s_list[ui];
-      const float4 *S = reinterpret_cast<const float4 *>(inv_covars_packed + (size_t)c * IV_PACKED);
-      float4 *dst = reinterpret_cast<float4 *>(s_S[ui % IV_POST_STAGES]);
-      for (int e = threadIdx.x; e < IV_PACKED / 4; e += blockDim.x)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + e)), "l"(S + e) : "memory");
-      if (threadIdx.x < FB_DIM / 4)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                     ::"r"((unsigned)__cvta_generic_to_shared(reinterpret_cast<float4 *>(s_mic[ui % IV_POST_STAGES]) + threadIdx.x)),
-                       "l"(reinterpret_cast<const float4 *>(means_invcovars + (size_t)c * FB_DIM) + threadIdx.x) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");      // (possibly empty) group: keeps the group count uniform
+  for (int i = threadIdx.x; i < n_union; i += blockDim.x) s_gc[i] = gconsts[s_list[i]];      // not a global load per loop trip
+  __syncthreads();
+  // Staging: thread 0 streams the union's components through the ring with two bulk copies each (packed inverse
+  // covariance, 10.5 KB, and mean x inverse covariance, 288 B) that complete on the slot's "full" mbarrier; every warp
+  // waits for it -- also the warps whose row did not select the component, which keeps all of them within one ring round
+  // -- and releases the slot on its "empty" mbarrier.  No CTA-wide barrier and no per-thread staging instructions (the
+  // cp.async version spent more issue slots on staging and __syncthreads than on the quadratic forms: ncu 190 M
+  // instructions for ~50 M of arithmetic).  A separate producer warp was measured slower: 9 warps of 110 registers do not
+  // fit twice into the SM's four register files, and one CTA per SM cannot hide the L2 round trips.
+  const uint32_t full0 = tma_smem_u32(s_bar), empty0 = tma_smem_u32(s_bar + IV_POST_STAGES);
+  auto issue = [&](int ui) {
+    if (ui >= n_union) return;
+    const int slot = ui % IV_POST_STAGES, round = ui / IV_POST_STAGES;
+    if (round > 0) tma_bar_wait(empty0 + 8 * slot, (round - 1) & 1);
+    const int c = s_list[ui];
+    tma_bar_expect_tx(full0 + 8 * slot, IV_ENT * 4);
+    tma_bulk_g2s(tma_smem_u32(s_S[slot]), inv_covars_packed + (size_t)c * IV_PACKED, IV_PACKED * 4, full0 + 8 * slot);
+    tma_bulk_g2s(tma_smem_u32(s_S[slot] + IV_PACKED), means_invcovars + (size_t)c * FB_DIM, FB_DIM * 4, full0 + 8 * slot);
   };
+  if (threadIdx.x == 0)
+    for (int u0 = 0; u0 < IV_POST_STAGES - 1; ++u0) issue(u0);
   float my_ll = -INFINITY;
-#pragma unroll
-  for (int s0 = 0; s0 < IV_POST_STAGES - 1; ++s0) stage(s0);
   for (int ui = 0; ui < n_union; ++ui) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(IV_POST_STAGES - 2) : "memory");   // this thread's part of component ui landed
-    __syncthreads();                                  // ... everybody's did, and everybody finished component ui - 1
-    stage(ui + IV_POST_STAGES - 1);                   // into the buffer component ui - 1 used
+    const int slot = ui % IV_POST_STAGES;
     const int c = s_list[ui];
     const int pos = __ffs(__ballot_sync(0xffffffffu, sel == c)) - 1;
+    if (threadIdx.x == 0) issue(ui + IV_POST_STAGES - 1);            // into the slot component ui - 1 used
+    tma_bar_wait(full0 + 8 * slot, (ui / IV_POST_STAGES) & 1);
     if (pos >= 0) {
-      const float *S = s_S[ui % IV_POST_STAGES];
-      float q = 0.f;
+      const float *S = s_S[slot];
+      const float2 *S2 = reinterpret_cast<const float2 *>(S) + lane;
+      float2 q2 = make_float2(0.f, 0.f), q3 = make_float2(0.f, 0.f);      // two chains: FFMA2 latency
 #pragma unroll
-      for (int m = 0; m < IV_XX_REGS; ++m) {
-        const int e = lane + 32 * m;
-        if (e < IV_PACKED) q += S[e] * xx[m];
+      for (int m = 0; m < IV_XX_PAIRS; ++m) {
+        // only the last pair index is partly outside the block (xx is zero there, but the buffer holds no defined value)
+        if (64 * m + 63 < IV_ENT || 2 * lane + 64 * m < IV_ENT) {
+          if (m & 1) q3 = __ffma2_rn(S2[32 * m], xx[m], q3);
+          else q2 = __ffma2_rn(S2[32 * m], xx[m], q2);
+        }
       }
-      float lin = 0.f;
-      for (int d = lane; d < FB_DIM; d += 32) lin += s_mic[ui % IV_POST_STAGES][d] * s_x[w][d];
-      float tot = lin - q;
+      float tot = -((q2.x + q3.x) + (q2.y + q3.y));    // lin - q
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-      if (lane == pos) my_ll = gconsts[c] + tot;
+      if (lane == pos) my_ll = s_gc[ui] + tot;
     }
+    __syncwarp();
+    if (lane == 0) tma_bar_arrive(empty0 + 8 * slot);
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (row < 0) return;
   // softmax / pruning, exactly as in fgmm_post_kernel
   float m = my_ll;
@@ -674,6 +699,131 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
     }
 }
 
+// The same sum with the rows of U staged by the TMA engine (used whenever n_packed is a multiple of 4, i.e. 16-byte
+// aligned row segments).  ncu of the kernel above at C3: 282 us, issue slots 32 % busy, 5.4 warps stalled on global loads per
+// issued instruction -- a thread loads four rows, waits, then runs its 128 DFMAs, and with 126 registers only 16 warps per SM
+// hide that.  Here one thread streams the active rows (one bulk copy of this CTA's column segment per component, four
+// components per stage, IV_QUAD_STAGES stages in flight, completion on mbarriers) while 8 consumer warps only read shared
+// memory and feed the FP64 pipe; the gammas of the next 64 components are prefetched into registers during the current
+// 64.  Grid (b-chunks, column blocks): the CTAs of one column block run side by side, so its rows come from HBM once and
+// from L2 for the other utterance chunks.  Arithmetic and summation order per entry are those of the kernel above.
+#define IV_QUAD_STAGES 6
+#define IV_QUAD_STAGE_COMPS 4
+#define IV_QUAD_COLS 256
+#define IV_QUAD_RING_BYTES (IV_QUAD_STAGES * IV_QUAD_STAGE_COMPS * IV_QUAD_COLS * 4)
+#define IV_QUAD_G_BYTES (64 * IV_BCHUNK * 8)
+static inline size_t ivec_quad_tma_smem(int C) { return IV_QUAD_RING_BYTES + IV_QUAD_G_BYTES + 2 * IV_QUAD_STAGES * 8 + ((size_t)C + 4) * 4; }
+
+__global__ void __launch_bounds__(256, 2)
+ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gamma, const int *__restrict__ act_list, int B, int C,
+                     int n_packed, double *__restrict__ quad, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  extern __shared__ __align__(128) unsigned char q_smem[];
+  float *ring = reinterpret_cast<float *>(q_smem);
+  double (*s_g)[IV_BCHUNK] = reinterpret_cast<double (*)[IV_BCHUNK]>(q_smem + IV_QUAD_RING_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(q_smem + IV_QUAD_RING_BYTES + IV_QUAD_G_BYTES);
+  int *s_list = reinterpret_cast<int *>(bars + 2 * IV_QUAD_STAGES);
+  const uint32_t full0 = tma_smem_u32(bars), empty0 = tma_smem_u32(bars + IV_QUAD_STAGES);
+  const int b0 = blockIdx.x * IV_BCHUNK;
+  const int nb = min(IV_BCHUNK, B - b0);
+  const int col0 = blockIdx.y * IV_QUAD_COLS;
+  const int *list = act_list + (size_t)blockIdx.x * (C + 1);
+  const int n_act = list[0];
+  for (int i = threadIdx.x; i < n_act; i += blockDim.x) s_list[i] = list[1 + i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < IV_QUAD_STAGES; ++s) {
+      tma_bar_init(full0 + 8 * s, 1);
+      tma_bar_init(empty0 + 8 * s, 8);                // one arrival per consumer warp
+    }
+    tma_bar_init_fence();
+  }
+  __syncthreads();
+  const int n_stages = (n_act + IV_QUAD_STAGE_COMPS - 1) / IV_QUAD_STAGE_COMPS;
+  const int lane = threadIdx.x & 31;
+  // thread 0 is also the producer: stage st + IV_QUAD_STAGES - 1 is issued right before stage st is consumed, into the slot
+  // that stage st - 1 used (its "empty" barrier completes when all 8 warps have released it).  A separate producer warp
+  // (288 threads) costs the second CTA per SM: 9 warps do not split evenly over the 4 sub-partitions' register files.
+  const uint32_t seg_bytes = (uint32_t)min(IV_QUAD_COLS, n_packed - col0) * 4u;
+  const uint32_t ring0 = tma_smem_u32(ring);
+  auto issue = [&](int st) {
+    if (st >= n_stages) return;
+    const int slot = st % IV_QUAD_STAGES, round = st / IV_QUAD_STAGES;
+    if (round > 0) tma_bar_wait(empty0 + 8 * slot, (round - 1) & 1);
+    const int nc = min(IV_QUAD_STAGE_COMPS, n_act - st * IV_QUAD_STAGE_COMPS);
+    tma_bar_expect_tx(full0 + 8 * slot, nc * seg_bytes);
+    for (int k = 0; k < nc; ++k)
+      tma_bulk_g2s(ring0 + (uint32_t)((slot * IV_QUAD_STAGE_COMPS + k) * IV_QUAD_COLS * 4),
+                   U + (size_t)s_list[st * IV_QUAD_STAGE_COMPS + k] * n_packed + col0, seg_bytes, full0 + 8 * slot);
+  };
+  if (threadIdx.x == 0)
+    for (int st0 = 0; st0 < IV_QUAD_STAGES - 1; ++st0) issue(st0);
+  const int ug = threadIdx.x >> 6, cg = threadIdx.x & 63;
+  const int e0 = col0 + cg * 4;
+  const bool work = ug * 8 < nb;                      // warp-uniform: utterance groups beyond the batch skip the arithmetic
+  double acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  // gamma gather of a 64-component chunk: element idx = threadIdx.x + 256 q -> component idx / 32, utterance idx % 32
+  double gnext[8];
+  auto gather = [&](int a0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = threadIdx.x + 256 * q, k = idx / IV_BCHUNK, i = idx - k * IV_BCHUNK;
+      gnext[q] = (i < nb && a0 + k < n_act) ? gamma[(size_t)(b0 + i) * C + s_list[a0 + k]] : 0.0;
+    }
+  };
+  gather(0);
+  int st = 0;
+  for (int a0 = 0; a0 < n_act; a0 += 64) {
+    const int n = min(64, n_act - a0);
+    __syncthreads();                                  // everybody finished reading the previous chunk's gammas
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = threadIdx.x + 256 * q;
+      s_g[idx / IV_BCHUNK][idx % IV_BCHUNK] = gnext[q];
+    }
+    __syncthreads();
+    if (a0 + 64 < n_act) gather(a0 + 64);
+    for (int k0 = 0; k0 < n; k0 += IV_QUAD_STAGE_COMPS, ++st) {
+      const int slot = st % IV_QUAD_STAGES;
+      if (threadIdx.x == 0) issue(st + IV_QUAD_STAGES - 1);
+      tma_bar_wait(full0 + 8 * slot, (st / IV_QUAD_STAGES) & 1);
+      if (work) {
+        const float4 *r = reinterpret_cast<const float4 *>(ring + (size_t)slot * IV_QUAD_STAGE_COMPS * IV_QUAD_COLS) + cg;
+#pragma unroll
+        for (int kk = 0; kk < IV_QUAD_STAGE_COMPS; ++kk) {
+          if (k0 + kk < n) {
+            const float4 pv = r[kk * (IV_QUAD_COLS / 4)];
+            const float p[4] = {pv.x, pv.y, pv.z, pv.w};
+            const double2 *gr = reinterpret_cast<const double2 *>(&s_g[k0 + kk][ug * 8]);
+            const double2 g01 = gr[0], g23 = gr[1], g45 = gr[2], g67 = gr[3];
+            const double gv[8] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y, g67.x, g67.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[i][j] += (double)p[i] * gv[j];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tma_bar_arrive(empty0 + 8 * slot);
+    }
+  }
+  if (work && e0 < n_packed) {                         // n_packed % 4 == 0: a thread's four entries are inside or outside together
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int bi = ug * 8 + j;
+      if (bi < nb) {
+        double2 *dst = reinterpret_cast<double2 *>(quad + (size_t)(b0 + bi) * n_packed + e0);
+        dst[0] = make_double2(acc[0][j], acc[1][j]);
+        dst[1] = make_double2(acc[2][j], acc[3][j]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Per utterance: A = unpack(quad) + I, rhs = sum of lin partials (+ prior offset on element 0), right-looking blocked
 // Cholesky (block 32) with the right-hand side carried as an extra matrix row, so the forward substitution falls out of the
@@ -697,7 +847,7 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
                   const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
 #ifdef IV_SOLVE_STATS
-  long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long st[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long st_t = clock64();
 #define IV_LAP(i) do { const long long n_ = clock64(); st[i] += n_ - st_t; st_t = n_; } while (0)
 #else
@@ -708,6 +858,7 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   double *invd = s_dyn + R;                          // [R]   1 / L[k][k]
   double *panel = s_dyn + 2 * R;                     // [R + 2][IV_PSTRIDE]: rows k0..R-1 of the block column, the rhs row, a zero row
   __shared__ double s_l11[IV_NB][IV_PSTRIDE];        // factored diagonal block, identity-padded to 32 x 32
+  __shared__ double s_a[IV_NB][IV_PSTRIDE];          // its unscaled working copy
   __shared__ double s_invd[IV_NB];
   __shared__ double s_blk[IV_NB];
   __shared__ int s_fail;
@@ -722,8 +873,13 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   const double *qb = quad + (size_t)b * n_packed;
   for (int r = tid; r < R; r += nt) {
     double acc = 0.0;
-#pragma unroll 8
-    for (int s = 0; s < n_splits; ++s) acc += lin_part[((size_t)s * B + b) * R + r];
+    for (int s0 = 0; s0 < n_splits; s0 += 32) {      // 32 partials in flight (the plain loop ran at one L2 round trip per 4);
+      double v[32];                                  // the additions keep their order (+ 0.0 beyond the last split)
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] = (s0 + q < n_splits) ? __ldg(lin_part + ((size_t)(s0 + q) * B + b) * R + r) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) acc += v[q];
+    }
     rhs[r] = acc + ((r == 0) ? prior_offset : 0.0);
   }
   __syncthreads();
@@ -744,7 +900,7 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
         panel[i * IV_PSTRIDE + j] = use ? v + ((i == j) ? 1.0 : 0.0) : 0.0;
       }
     } else {
-#pragma unroll 8
+#pragma unroll 13
       for (int idx = tid; idx < rows * IV_NB; idx += nt) {
         const int i = idx >> 5, j = idx & 31;
         const bool use = j < nbk && j <= i;
@@ -758,37 +914,41 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
     }
     __syncthreads();
     IV_LAP(1);
-    // ---- diagonal block: warp 0, row `lane` in registers (identity padding for nbk < 32)
-    if (warp == 0) {
-      double l[IV_NB];
-#pragma unroll
-      for (int k = 0; k < IV_NB; ++k)
-        l[k] = (lane < nbk && k < nbk) ? ((k <= lane) ? panel[lane * IV_PSTRIDE + k] : 0.0) : ((k == lane) ? 1.0 : 0.0);
+    // ---- diagonal block (identity padding for nbk < 32), all warps: right-looking, one barrier per column.  The working
+    // copy s_a stays UNSCALED -- a_ij -= a_ik a_jk / a_kk -- so that within a column step nobody reads what somebody else
+    // writes; L_ik = a_ik / sqrt(a_kk) goes to s_l11.  (One warp with the rows in registers and shuffles took 29.6 k
+    // cycles per block, a third of the kernel, with the other 15 warps waiting at the barrier.)
+    {
+      const int p0 = tid, p1 = tid + 512;              // two of the 32 x 32 positions per thread
+      const int i0 = p0 >> 5, j0 = p0 & 31, i1 = (p1 >> 5) & 31, j1 = p1 & 31;
+      auto init = [&](int i, int j) {
+        s_a[i][j] = (i < nbk && j < nbk) ? ((j <= i) ? panel[i * IV_PSTRIDE + j] : 0.0) : ((i == j) ? 1.0 : 0.0);
+        s_l11[i][j] = 0.0;
+      };
+      init(i0, j0);
+      init(i1, j1);
+      __syncthreads();
       bool ok = true;
-      double my_inv = 1.0;
-#pragma unroll
       for (int k = 0; k < IV_NB; ++k) {
-        const double akk = __shfl_sync(0xffffffffu, l[k], k);
+        const double akk = s_a[k][k];
         if (!(akk > 0.0)) ok = false;
-        const double inv = rsqrt(akk);
-        if (lane == k) { l[k] = akk * inv; my_inv = inv; }
-        else if (lane > k) l[k] *= inv;
-#pragma unroll
-        for (int j = 0; j < IV_NB; ++j) {             // constant trip count so that the nest unrolls fully (l[] stays in registers)
-          if (j > k) {
-            const double ljk = __shfl_sync(0xffffffffu, l[k], j);
-            if (lane >= j) l[j] -= l[k] * ljk;
+        const double inv = rsqrt(akk), inv2 = inv * inv;
+        auto step = [&](int i, int j) {
+          if (j == k && i >= k) {
+            s_l11[i][k] = (i == k) ? akk * inv : s_a[i][k] * inv;
+            if (i == k) { s_invd[k] = inv; if (k < nbk) invd[k0 + k] = inv; }
+          } else if (j > k && i >= j) {
+            s_a[i][j] -= s_a[i][k] * s_a[j][k] * inv2;
           }
-        }
+        };
+        step(i0, j0);
+        step(i1, j1);
+        __syncthreads();
       }
-      if (!ok && lane == 0) s_fail = 1;
-#pragma unroll
-      for (int k = 0; k < IV_NB; ++k) {
-        s_l11[lane][k] = (k <= lane) ? l[k] : 0.0;
-        if (lane < nbk && k <= lane && k < nbk) panel[lane * IV_PSTRIDE + k] = l[k];
-      }
-      s_invd[lane] = my_inv;
-      if (lane < nbk) invd[k0 + lane] = my_inv;
+      if (!ok && tid == 0) s_fail = 1;
+      auto back = [&](int i, int j) { if (i < nbk && j <= i) panel[i * IV_PSTRIDE + j] = s_l11[i][j]; };
+      back(i0, j0);
+      back(i1, j1);
     }
     __syncthreads();
     IV_LAP(2);
@@ -853,11 +1013,21 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
         for (int x = 0; x < 8; ++x) ri[x] = ((i0 + x < rows) ? i0 + x : zrow) * IV_PSTRIDE;
 #pragma unroll
         for (int y = 0; y < 4; ++y) rj[y] = ((j0 + lane + 32 * y < rows) ? j0 + lane + 32 * y : zrow) * IV_PSTRIDE;
+        // c starts as the old trailing values (their 32 L2 loads are in flight together and overlap the first panel reads;
+        // loaded after the products they cost a second, exposed, round trip per tile) and the products are subtracted
         double c[8][4];
 #pragma unroll
         for (int x = 0; x < 8; ++x)
 #pragma unroll
-          for (int y = 0; y < 4; ++y) c[x][y] = 0.0;
+          for (int y = 0; y < 4; ++y) {
+            const int li = i0 + x, lj = j0 + lane + 32 * y;
+            double old = 0.0;
+            if (li < rows && lj <= li)
+              old = (k0 == 0) ? __ldg(qb + (size_t)li * (li + 1) / 2 + lj) + ((li == lj) ? 1.0 : 0.0)
+                              : __ldcg(A + (size_t)(k0 + li) * R + k0 + lj);
+            c[x][y] = old;
+          }
+        IV_LAP(7);
 #pragma unroll 8
         for (int q = 0; q < IV_NB; ++q) {
           double av[8], bv[4];
@@ -868,24 +1038,23 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
 #pragma unroll
           for (int x = 0; x < 8; ++x)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) c[x][y] += av[x] * bv[y];
+            for (int y = 0; y < 4; ++y) c[x][y] = fma(-av[x], bv[y], c[x][y]);
         }
+        IV_LAP(8);
 #pragma unroll
         for (int x = 0; x < 8; ++x)
 #pragma unroll
           for (int y = 0; y < 4; ++y) {
             const int li = i0 + x, lj = j0 + lane + 32 * y;
-            if (li < rows && lj <= li) {
-              double *dst = A + (size_t)(k0 + li) * R + k0 + lj;
-              const double old = (k0 == 0) ? qb[(size_t)li * (li + 1) / 2 + lj] + ((li == lj) ? 1.0 : 0.0) : *dst;
-              *dst = old - c[x][y];
-            }
+            if (li < rows && lj <= li) A[(size_t)(k0 + li) * R + k0 + lj] = c[x][y];
           }
+        IV_LAP(9);
       }
     }
+    IV_LAP(5);
     if (csize > 1) cluster.sync();                   // the partner's trailing-update tiles are visible (release / acquire)
     else __syncthreads();
-    IV_LAP(5);
+    IV_LAP(10);
   }
   // rhs now holds y = L^-1 b.  Backward substitution L^T w = y, blocked from the last block.
   const int n_blocks = (R + IV_NB - 1) / IV_NB;
@@ -906,12 +1075,17 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
           if (lane < k) wv -= lcol[k] * wk;
         }
       }
-      if (lane < nbk) { rhs[k0 + lane] = wv; s_blk[lane] = wv; }
+      if (lane < nbk) rhs[k0 + lane] = wv;
+      s_blk[lane] = (lane < nbk) ? wv : 0.0;
     }
     __syncthreads();
     for (int i = tid; i < k0; i += nt) {
+      double a[IV_NB];                                 // the block's 32 loads in flight together
+#pragma unroll
+      for (int j = 0; j < IV_NB; ++j) a[j] = (j < nbk) ? __ldcg(A + (size_t)(k0 + j) * R + i) : 0.0;
       double v = rhs[i];
-      for (int j = 0; j < nbk; ++j) v -= A[(size_t)(k0 + j) * R + i] * s_blk[j];
+#pragma unroll
+      for (int j = 0; j < IV_NB; ++j) v -= a[j] * s_blk[j];
       rhs[i] = v;
     }
     __syncthreads();
@@ -919,8 +1093,8 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   IV_LAP(6);
 #ifdef IV_SOLVE_STATS
   if (b == 0 && (tid == 0 || tid == 511))
-    printf("solve tid %d clk: init %lld load %lld diag %lld l21 %lld rhs+wb %lld trailing %lld backsub %lld\n", tid, st[0], st[1], st[2], st[3],
-           st[4], st[5], st[6]);
+    printf("solve tid %d clk: init %lld load %lld diag %lld l21 %lld rhs+wb %lld trailing: setup %lld fma %lld rmw %lld rest %lld sync %lld; backsub %lld\n",
+           tid, st[0], st[1], st[2], st[3], st[4], st[7], st[8], st[9], st[5], st[10], st[6]);
 #endif
   if (crank == 0)
     for (int r = tid; r < R; r += nt) ivec[(size_t)b * R + r] = (float)(rhs[r] - ((r == 0) ? prior_offset : 0.0));
@@ -1294,8 +1468,19 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
                                                                           v->n_splits, v->lin_part.p, done_flag);
   fb_prof_mark(ctx, 11);
   nv.next("fb:ivec_quad");
-  ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, v->act_list.p, B, v->C,
-                                                                                   v->n_packed, v->quad.p, done_flag);
+  static const bool plain_quad = getenv("FB_IV_PLAIN_QUAD") != nullptr;       // diagnostic: the register-staged kernel
+  if ((v->n_packed & 3) == 0 && !plain_quad) {
+    static std::atomic<unsigned long long> attr_quad_mask{0};
+    if (fb_once_per_device(attr_quad_mask, ctx->device)) {
+      FB_CUDA(cudaFuncSetAttribute(ivec_quad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    }
+    if (ivec_quad_tma_smem(v->C) > 100 * 1024) return FB_ERR_ARG;
+    ivec_quad_tma_kernel<<<dim3(bch, fb_div_up(v->n_packed, IV_QUAD_COLS)), 256, ivec_quad_tma_smem(v->C), ctx->stream>>>(
+        v->U.p, v->gamma.p, v->act_list.p, B, v->C, v->n_packed, v->quad.p, done_flag);
+  } else {
+    ivec_quad_kernel<<<dim3(fb_div_up(v->n_packed, 256), bch), 256, 0, ctx->stream>>>(v->U.p, v->gamma.p, v->act_list.p, B, v->C,
+                                                                                     v->n_packed, v->quad.p, done_flag);
+  }
   fb_prof_mark(ctx, 12);
   nv.next("fb:ivec_solve");
   const size_t smem_solve = (2 * (size_t)v->R + ((size_t)v->R + 2) * IV_PSTRIDE) * sizeof(double);

@@ -409,7 +409,7 @@ def test_library_contains_sm100a_tensor_core_and_tma_code():
         pytest.skip("cuobjdump or the built library is not available")
     elf = subprocess.run([cuobjdump, "--list-elf", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
     assert "sm_100a" in elf, elf[:400]
-    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_Z15gmm_umma_kernelILb0ELb1EEv7GmmArgs", _lib.LIB_PATH],
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_Z15gmm_umma_kernelILb0ELb1ELi0EEv7GmmArgs", _lib.LIB_PATH],
                           capture_output=True, text=True, timeout=300).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTCCP", "UBLKCP", "SYNCS.PHASECHK"):
         assert mnemonic in sass, mnemonic
