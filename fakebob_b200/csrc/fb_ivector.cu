@@ -858,7 +858,8 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   double *invd = s_dyn + R;                          // [R]   1 / L[k][k]
   double *panel = s_dyn + 2 * R;                     // [R + 2][IV_PSTRIDE]: rows k0..R-1 of the block column, the rhs row, a zero row
   __shared__ double s_l11[IV_NB][IV_PSTRIDE];        // factored diagonal block, identity-padded to 32 x 32
-  __shared__ double s_a[IV_NB][IV_PSTRIDE];          // its unscaled working copy
+  __shared__ double s_a[IV_NB][IV_PSTRIDE];          // working copy during its factorisation
+  __shared__ __align__(16) double s_l11t[IV_NB][IV_NB + 2];   // [q][j] = L[j][q] / L[j][j]: one FMA per substitution step, read in pairs
   __shared__ double s_invd[IV_NB];
   __shared__ double s_blk[IV_NB];
   __shared__ int s_fail;
@@ -914,41 +915,94 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
     }
     __syncthreads();
     IV_LAP(1);
-    // ---- diagonal block (identity padding for nbk < 32), all warps: right-looking, one barrier per column.  The working
-    // copy s_a stays UNSCALED -- a_ij -= a_ik a_jk / a_kk -- so that within a column step nobody reads what somebody else
-    // writes; L_ik = a_ik / sqrt(a_kk) goes to s_l11.  (One warp with the rows in registers and shuffles took 29.6 k
-    // cycles per block, a third of the kernel, with the other 15 warps waiting at the barrier.)
+    // ---- diagonal block (identity padding for nbk < 32), in four 8-column sub-blocks.  The serial part of a Cholesky
+    // factorisation is one rsqrt + update chain per column; here that chain runs without any communication: every lane
+    // of warp 0 factors the 8 x 8 diagonal sub-block redundantly in its own registers, then lane l solves row l below it
+    // against that register copy.  All warps then apply the rank-8 update to the rest of the block (two positions per
+    // thread).  Two barriers per sub-block instead of one per column.  (Cycles per 32 x 32 block: 29.6 k for one warp with
+    // the rows in registers and a shuffle per element, 17 k for all warps with a barrier per column, ~6 k this way.)
     {
-      const int p0 = tid, p1 = tid + 512;              // two of the 32 x 32 positions per thread
-      const int i0 = p0 >> 5, j0 = p0 & 31, i1 = (p1 >> 5) & 31, j1 = p1 & 31;
-      auto init = [&](int i, int j) {
-        s_a[i][j] = (i < nbk && j < nbk) ? ((j <= i) ? panel[i * IV_PSTRIDE + j] : 0.0) : ((i == j) ? 1.0 : 0.0);
-        s_l11[i][j] = 0.0;
+      const int ia = tid >> 5, ja = tid & 31, ib = ia + 16, jb = ja;      // positions tid and tid + 512
+      auto initial = [&](int i, int j) {
+        return (i < nbk && j < nbk) ? ((j <= i) ? panel[i * IV_PSTRIDE + j] : 0.0) : ((i == j) ? 1.0 : 0.0);
       };
-      init(i0, j0);
-      init(i1, j1);
+      s_a[ia][ja] = initial(ia, ja);
+      s_a[ib][jb] = initial(ib, jb);
+      s_l11[ia][ja] = 0.0;
+      s_l11[ib][jb] = 0.0;
       __syncthreads();
       bool ok = true;
-      for (int k = 0; k < IV_NB; ++k) {
-        const double akk = s_a[k][k];
-        if (!(akk > 0.0)) ok = false;
-        const double inv = rsqrt(akk), inv2 = inv * inv;
-        auto step = [&](int i, int j) {
-          if (j == k && i >= k) {
-            s_l11[i][k] = (i == k) ? akk * inv : s_a[i][k] * inv;
-            if (i == k) { s_invd[k] = inv; if (k < nbk) invd[k0 + k] = inv; }
-          } else if (j > k && i >= j) {
-            s_a[i][j] -= s_a[i][k] * s_a[j][k] * inv2;
+#pragma unroll 1
+      IV_LAP(11);
+      for (int kb = 0; kb < IV_NB; kb += 8) {
+        if (warp == 0) {
+          double d[8][8];                                // lower triangle of the sub-block, the same in every lane
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) d[r][c] = s_a[kb + r][kb + c];
+          double x[8];                                   // this lane's row below the sub-block
+          const int xi = kb + 8 + lane;
+          const bool has_row = xi < IV_NB;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) x[c] = has_row ? s_a[xi][kb + c] : 0.0;
+          double dinv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (!(d[c][c] > 0.0)) ok = false;
+            const double inv = rsqrt(d[c][c]);
+            dinv[c] = inv;
+            d[c][c] *= inv;
+#pragma unroll
+            for (int r = c + 1; r < 8; ++r) d[r][c] *= inv;
+#pragma unroll
+            for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+              for (int r = c2; r < 8; ++r) d[r][c2] = fma(-d[r][c], d[c2][c], d[r][c2]);
+            x[c] *= inv;
+#pragma unroll
+            for (int c2 = c + 1; c2 < 8; ++c2) x[c2] = fma(-x[c], d[c2][c], x[c2]);
           }
-        };
-        step(i0, j0);
-        step(i1, j1);
+          // publish: lane r < 8 writes row r of the factored sub-block, every lane its solved row
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (lane == r) {
+#pragma unroll
+              for (int c = 0; c <= r; ++c) {
+                s_l11[kb + r][kb + c] = d[r][c];
+                if (kb + r < nbk) panel[(kb + r) * IV_PSTRIDE + kb + c] = d[r][c];
+              }
+              s_invd[kb + r] = dinv[r];
+              if (kb + r < nbk) invd[k0 + kb + r] = dinv[r];
+            }
+          if (has_row) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              s_l11[xi][kb + c] = x[c];
+              if (xi < nbk) panel[xi * IV_PSTRIDE + kb + c] = x[c];
+            }
+          }
+        }
         __syncthreads();
+        IV_LAP(2);
+        if (kb + 8 < IV_NB) {                            // rank-8 update of the remaining lower triangle
+          auto update = [&](int i, int j) {
+            if (j >= kb + 8 && i >= j) {
+              double v = s_a[i][j];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) v = fma(-s_l11[i][kb + c], s_l11[j][kb + c], v);
+              s_a[i][j] = v;
+            }
+          };
+          if (ia >= kb + 8) update(ia, ja);              // warp-uniform: rows above the remaining block skip the loads
+          update(ib, jb);
+          __syncthreads();
+        }
+        IV_LAP(11);
       }
       if (!ok && tid == 0) s_fail = 1;
-      auto back = [&](int i, int j) { if (i < nbk && j <= i) panel[i * IV_PSTRIDE + j] = s_l11[i][j]; };
-      back(i0, j0);
-      back(i1, j1);
+      s_l11t[ja][ia] = s_l11[ia][ja] * s_invd[ia];
+      s_l11t[jb][ib] = s_l11[ib][jb] * s_invd[ib];
     }
     __syncthreads();
     IV_LAP(2);
@@ -961,16 +1015,19 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
       double *row = panel + i * IV_PSTRIDE;
       double x[IV_NB];
 #pragma unroll
-      for (int j = 0; j < IV_NB; ++j) x[j] = row[j];
+      for (int j = 0; j < IV_NB; ++j) x[j] = row[j] * s_invd[j];
       // column-oriented: once x[q] is final, every later entry takes its update (31 - q independent FMAs); the empty asm
       // keeps the compiler from hoisting all 496 broadcast loads of L11 to the top (it spilled 4 KB per thread)
 #pragma unroll
       for (int q = 0; q < IV_NB; ++q) {
-        x[q] *= s_invd[q];
         asm volatile("" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < IV_NB; ++j)
-          if (j > q) x[j] -= x[q] * s_l11[j][q];
+        for (int jj = 0; jj < IV_NB / 2; ++jj)
+          if (2 * jj + 1 > q) {                        // the phase is bound by these broadcast loads: two entries per load
+            const double2 l2 = *reinterpret_cast<const double2 *>(&s_l11t[q][2 * jj]);
+            if (2 * jj > q) x[2 * jj] = fma(-x[q], l2.x, x[2 * jj]);
+            x[2 * jj + 1] = fma(-x[q], l2.y, x[2 * jj + 1]);
+          }
       }
 #pragma unroll
       for (int j = 0; j < IV_NB; ++j) row[j] = x[j];
@@ -1067,12 +1124,15 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
 #pragma unroll
       for (int k = 0; k < IV_NB; ++k) lcol[k] = (k < nbk && lane < k) ? A[(size_t)(k0 + k) * R + k0 + lane] : 0.0;
       const double my_inv = (lane < nbk) ? invd[k0 + lane] : 1.0;
+      // w_lane = y_lane / L_ll - sum_k (L[k][lane] / L_ll) w_k: with the column pre-scaled a step is one shuffle + one FMA
+      wv *= my_inv;
+#pragma unroll
+      for (int k = 0; k < IV_NB; ++k) lcol[k] *= my_inv;
 #pragma unroll
       for (int k = IV_NB - 1; k >= 0; --k) {
         if (k < nbk) {
-          const double wk = __shfl_sync(0xffffffffu, wv * my_inv, k);
-          if (lane == k) wv = wk;
-          if (lane < k) wv -= lcol[k] * wk;
+          const double wk = __shfl_sync(0xffffffffu, wv, k);
+          if (lane < k) wv = fma(-lcol[k], wk, wv);
         }
       }
       if (lane < nbk) rhs[k0 + lane] = wv;
@@ -1093,8 +1153,8 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   IV_LAP(6);
 #ifdef IV_SOLVE_STATS
   if (b == 0 && (tid == 0 || tid == 511))
-    printf("solve tid %d clk: init %lld load %lld diag %lld l21 %lld rhs+wb %lld trailing: setup %lld fma %lld rmw %lld rest %lld sync %lld; backsub %lld\n",
-           tid, st[0], st[1], st[2], st[3], st[4], st[7], st[8], st[9], st[5], st[10], st[6]);
+    printf("solve tid %d clk: init %lld load %lld diag %lld l21 %lld rhs+wb %lld trailing: setup %lld fma %lld rmw %lld rest %lld sync %lld; backsub %lld; diag init+update %lld\n",
+           tid, st[0], st[1], st[2], st[3], st[4], st[7], st[8], st[9], st[5], st[10], st[6], st[11]);
 #endif
   if (crank == 0)
     for (int r = tid; r < R; r += nt) ivec[(size_t)b * R + r] = (float)(rhs[r] - ((r == 0) ? prior_offset : 0.0));

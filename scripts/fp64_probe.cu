@@ -28,7 +28,33 @@ __global__ void __launch_bounds__(256) dmma_probe(int iters, double *out, double
   for (int i = 0; i < 4; ++i) s += c0[i] + c1[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// dependent-chain latencies (one warp): DFMA, rsqrt(double), shuffle of a double
+__global__ void latency_probe(int iters, double *out, long long *clk, double a, double b) {
+  double x = threadIdx.x + 1.5;
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) x = fma(x, a, b);
+  long long t1 = clock64();
+  double y = x;
+  for (int i = 0; i < iters; ++i) y = rsqrt(y) + 1.0;
+  long long t2 = clock64();
+  double z = y;
+  for (int i = 0; i < iters; ++i) z = __shfl_sync(0xffffffffu, z, (i + 1) & 31) + 1.0;
+  long long t3 = clock64();
+  float f = (float)z;
+  for (int i = 0; i < iters; ++i) f = fmaf(f, 1.0001f, 0.5f);
+  long long t4 = clock64();
+  out[threadIdx.x] = z + f;
+  if (threadIdx.x == 0) { clk[0] = t1 - t0; clk[1] = t2 - t1; clk[2] = t3 - t2; clk[3] = t4 - t3; }
+}
 int main() {
+  {
+    double *o; long long *c, h[4];
+    cudaMalloc(&o, 32 * 8); cudaMalloc(&c, 4 * 8);
+    latency_probe<<<1, 32>>>(4096, o, c, 1.0000001, 1e-9);
+    cudaMemcpy(h, c, 32, cudaMemcpyDeviceToHost);
+    printf("latency (clk / dependent op, one warp): DFMA %.1f, rsqrt(double)+DADD %.1f, shfl(double)+DADD %.1f, FFMA %.1f\n",
+           h[0] / 4096.0, h[1] / 4096.0, h[2] / 4096.0, h[3] / 4096.0);
+  }
   double *out;
   cudaMalloc(&out, 148 * 8 * 256 * sizeof(double));
   cudaEvent_t e0, e1;
