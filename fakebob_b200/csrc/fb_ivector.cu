@@ -29,13 +29,14 @@ int fb_run_gmm_store(fb_ctx *ctx, float *ll_out, const int *done_flag);
 // ------------------------------------------------------------------------------------------------
 // Top-20 Gaussian selection: one warp per frame; lanes hold C/32 values each (C <= 2048).
 // Ties resolve to the lower component index (stable descending sort).
-// Fast path: bisect a threshold below the row maximum until between 20 and 64 values pass it (a few counting passes),
-// compact those candidates into shared memory and rank them exactly (value descending, index ascending).  Rows where the
-// bisection does not settle (massive ties) take the plain 20-round arg-max selection.
+// Fast path: find a threshold that between 20 and 64 values pass (normally the 20th largest lane maximum, one counting
+// pass; else a bisection below the row maximum), compact those candidates into shared memory and rank them exactly
+// (value descending, index ascending).  Rows where no such threshold exists (massive ties) take the plain 20-round
+// arg-max selection.
 // ------------------------------------------------------------------------------------------------
 #define IV_CAND 64
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C, int *__restrict__ gsel,
                const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
@@ -51,28 +52,49 @@ gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C
 #pragma unroll
   for (int i = 0; i < 64; ++i) v[i] = (i < per) ? src[lane + 32 * i] : -INFINITY;
   float best = -INFINITY;
-  int bi = 0;
 #pragma unroll
-  for (int i = 0; i < 64; ++i)
-    if (v[i] > best) { best = v[i]; bi = i; }
+  for (int i = 0; i < 64; ++i) best = fmaxf(best, v[i]);
   float M = best;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
-  // ---- threshold bisection: delta_lo passes fewer than 20 values, delta_hi more than IV_CAND
-  float d_lo = 0.f, d_hi = -1.f, delta = 8.f, tau = 0.f;
-  int cnt = 0, mine = 0;
-  bool ok = false;
-  for (int it = 0; it < 24 && !ok; ++it) {
-    tau = M - delta;
-    mine = 0;
+  // ---- threshold.  First guess: the 20th largest of the 32 lane maxima (bitonic sort across the lanes) -- twenty distinct
+  // values are >= it, so at least 20 pass, and in a 2048-component log-likelihood row rarely more than a few dozen do.
+  // Only if more than IV_CAND pass, bisect between it and the row maximum (delta_lo passes fewer than 20, delta_hi more
+  // than IV_CAND values).
+  float srt = best;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) mine += (v[i] >= tau) ? 1 : 0;
+  for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, srt, j);
+      const bool up = ((lane & k) == 0) == ((lane & j) == 0);      // this lane keeps the smaller value
+      srt = up ? fminf(srt, other) : fmaxf(srt, other);
+    }
+  float tau = __shfl_sync(0xffffffffu, srt, 32 - IV_NSEL);          // ascending: position 12 holds the 20th largest
+  int cnt = 0, mine = 0;
+  unsigned m_lo = 0u, m_hi = 0u;                                    // which of this lane's 64 values pass
+  auto count_pass = [&]() {
+    m_lo = 0u; m_hi = 0u;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m_lo |= (v[i] >= tau) ? (1u << i) : 0u;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m_hi |= (v[32 + i] >= tau) ? (1u << i) : 0u;
+    mine = __popc(m_lo) + __popc(m_hi);
     cnt = mine;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (cnt < IV_NSEL) { d_lo = delta; delta = (d_hi > 0.f) ? 0.5f * (d_lo + d_hi) : 2.f * delta; }
-    else if (cnt > IV_CAND) { d_hi = delta; delta = 0.5f * (d_lo + d_hi); }
-    else ok = true;
+  };
+  count_pass();
+  bool ok = cnt <= IV_CAND;                                         // cnt >= IV_NSEL by construction
+  if (!ok) {
+    float d_lo = 0.f, d_hi = M - tau, delta = 0.5f * (M - tau);
+    for (int it = 0; it < 24 && !ok && d_hi > 0.f; ++it) {
+      tau = M - delta;
+      count_pass();
+      if (cnt < IV_NSEL) { d_lo = delta; delta = 0.5f * (d_lo + d_hi); }
+      else if (cnt > IV_CAND) { d_hi = delta; delta = 0.5f * (d_lo + d_hi); }
+      else ok = true;
+    }
   }
   if (ok) {
     int incl = mine;
@@ -82,9 +104,15 @@ gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C
       if (lane >= o) incl += up;
     }
     int pos = incl - mine;
-#pragma unroll
-    for (int i = 0; i < 64; ++i)
-      if (v[i] >= tau) { s_val[w][pos] = v[i]; s_idx[w][pos] = lane + 32 * i; ++pos; }
+    // a lane passes one or two values: walk its mask and re-read them (L1 / L2 hits) instead of testing all 64 registers
+    for (unsigned m = m_lo; m; m &= m - 1) {
+      const int i = __ffs(m) - 1;
+      s_val[w][pos] = src[lane + 32 * i]; s_idx[w][pos] = lane + 32 * i; ++pos;
+    }
+    for (unsigned m = m_hi; m; m &= m - 1) {
+      const int i = 32 + __ffs(m) - 1;
+      s_val[w][pos] = src[lane + 32 * i]; s_idx[w][pos] = lane + 32 * i; ++pos;
+    }
     __syncwarp();
 #pragma unroll
     for (int h = 0; h < IV_CAND / 32; ++h) {
@@ -102,6 +130,11 @@ gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C
     }
     return;
   }
+  int bi = 0;                                        // slow path: this lane's arg-max (first maximum)
+  best = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 64; ++i)
+    if (v[i] > best) { best = v[i]; bi = i; }
   for (int k = 0; k < IV_NSEL; ++k) {
     float wv = best;
     int wi = lane + 32 * bi;                      // component index
