@@ -228,22 +228,54 @@ fgmm_post_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Same arithmetic, rows grouped: one CTA handles the rows of EIGHT audios at the same frame index t, one warp per row.
+// Same quantity, rows grouped: one CTA handles the rows of EIGHT audios at the same frame index t.
 // The plain kernel above executes ~9 instructions per (row, component, packed entry) -- table lookup, two feature loads,
 // products, select -- and gathers 20 x 10.5 KB of packed inverse covariances per row from L2 (4.8 GB per NES iteration at
-// C3).  Here every lane keeps its 83 products x_r x_c (halved on the diagonal) of the row in REGISTERS, so a component costs
-// one shared-memory load and one FMA per entry, and each covariance is staged in shared memory once (cp.async, double
-// buffered) for all rows of the CTA that selected it: the audios of an NES batch are perturbations of one utterance, so
-// rows with the same frame index select (almost) the same components.  Any batch is handled correctly: rows that share no
-// component simply do not share loads.  Per row the operations and their order are those of fgmm_post_kernel.
+// C3).  Here
+//  * the audios of an NES batch are perturbations of one utterance, so rows with the same frame index select (almost) the
+//    same components: the CTA stages the UNION of its rows' selections, each component once (~25 instead of 8 x 20).  Any
+//    batch is handled correctly: rows that share no component simply do not share loads;
+//  * a component is staged as one block [packed inverse covariance | mean x inverse covariance] (2700 floats) by two bulk
+//    copies of the TMA engine that complete on the slot's "full" mbarrier (ring of IV_POST_STAGES slots, released through
+//    "empty" mbarriers; thread 0 issues stage ui + 3 right before it consumes stage ui -- a separate producer warp was
+//    measured slower: 9 warps of 110 registers do not fit twice into the SM's four register files);
+//  * the multipliers of a row -- x_r x_c (halved on the diagonal) against the covariance entries, -x_d against the linear
+//    entries, so one pass gives q - lin -- live in REGISTERS as pairs, one 64-bit shared-memory load + one packed FFMA2 per
+//    two entries;
+//  * warp w = (row group w / 4, entry slice w % 4): it multiplies ONE QUARTER of the staged block with FOUR rows, so a
+//    staged value is read from shared memory twice per CTA instead of once per selecting row (the row-per-warp version
+//    moved 5 GB through shared memory per launch, half of its run time).  The four slice partials of a (row, component)
+//    meet in shared memory (fixed order: deterministic) IV_COMB_LAG components later, combined by warp (component % 8).
+// Summation order differs from fgmm_post_kernel (float rounding only); selection, soft-max and pruning are the same.
 // ------------------------------------------------------------------------------------------------
 #define IV_GROUP 8
-#define IV_PACKED_PAD ((IV_PACKED + 3) & ~3)
 #define IV_ENT (IV_PACKED + FB_DIM)                 // a staged component: packed inverse covariance, then mean x inverse covariance
-#define IV_XX_PAIRS ((IV_ENT + 63) / 64)            // 43 register pairs per lane
-static_assert(IV_PACKED % 2 == 0 && IV_ENT % 2 == 0, "pairs of entries");
-#define IV_POST_STAGES 4                            // covariance blocks in flight: an L2 round trip (~1 us) per 0.3 us of compute
+#define IV_PAIRS (IV_ENT / 2)                       // 1350
+#define IV_ES 4                                     // entry slices
+#define IV_RPG (IV_GROUP / 2)                       // rows per row group (two row groups)
+#define IV_SLICE_PAIRS ((IV_PAIRS + IV_ES - 1) / IV_ES)        // 338
+#define IV_LP ((IV_SLICE_PAIRS + 31) / 32)          // 11 register pairs per lane and row
+#define IV_POST_STAGES 8                            // covariance blocks in flight (a bulk copy of 10.8 KB takes ~2 k cycles to land,
+                                                    // a component ~0.3 k cycles to consume: with 4 the warps waited 16 % of the time)
+#define IV_COMB_LAG 4                               // a component's partials are combined this many components later
+#define IV_PSLOTS 16                                // partial-sum slots, >= IV_POST_STAGES + IV_COMB_LAG (see the slot-reuse argument)
+static_assert(IV_PSLOTS >= IV_POST_STAGES + IV_COMB_LAG, "a partial slot must be combined before the ring lets anybody refill it");
 static_assert(IV_PACKED % 4 == 0 && FB_DIM % 4 == 0, "bulk copies need 16-byte aligned component blocks of 16 n bytes");
+static_assert(IV_PACKED % 2 == 0 && IV_ENT % 2 == 0, "pairs of entries");
+
+struct __align__(16) PostSmem {
+  float S[IV_POST_STAGES][IV_ENT];
+  float gc[IV_GROUP * IV_NSEL];
+  float x[IV_GROUP][FB_DIM];
+  float ll[IV_GROUP][IV_NSEL];
+  float part[IV_PSLOTS][2][IV_ES][IV_RPG];
+  unsigned bitmap[128];                             // C <= 4096
+  unsigned short prefix[128];                       // union members before bitmap word i
+  int list[IV_GROUP * IV_NSEL];
+  unsigned pos[IV_GROUP * IV_NSEL][2];              // per union member: byte r = position of it in row r's selection, 0xFF = not selected
+  uint64_t bar[2 * IV_POST_STAGES + IV_PSLOTS];
+  int n;
+};
 
 __global__ void __launch_bounds__(256, 2)
 fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, const float *__restrict__ gconsts,
@@ -252,25 +284,25 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
                        const int *__restrict__ vrank, const int *__restrict__ row_off, int B, int C, int n_chunks,
                        float min_post, float *__restrict__ post, const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  __shared__ __align__(16) float s_S[IV_POST_STAGES][IV_ENT];
-  __shared__ float s_gc[IV_GROUP * IV_NSEL];
-  __shared__ float s_x[IV_GROUP][FB_DIM];
-  __shared__ unsigned s_bitmap[128];                  // C <= 4096
-  __shared__ int s_list[IV_GROUP * IV_NSEL];
-  __shared__ int s_n;
-  __shared__ __align__(8) uint64_t s_bar[2 * IV_POST_STAGES];
+  extern __shared__ __align__(16) unsigned char post_smem_raw[];
+  PostSmem &sm = *reinterpret_cast<PostSmem *>(post_smem_raw);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = w / IV_ES, es = w % IV_ES;
   const int t = blockIdx.x / n_chunks, chunk = blockIdx.x - t * n_chunks;
+  const uint32_t full0 = tma_smem_u32(sm.bar), empty0 = tma_smem_u32(sm.bar + IV_POST_STAGES),
+                 pfull0 = tma_smem_u32(sm.bar + 2 * IV_POST_STAGES);
   if (threadIdx.x == 0) {
     for (int k = 0; k < IV_POST_STAGES; ++k) {
-      tma_bar_init(tma_smem_u32(s_bar + k), 1);
-      tma_bar_init(tma_smem_u32(s_bar + IV_POST_STAGES + k), IV_GROUP);      // one arrival per consumer warp
+      tma_bar_init(full0 + 8 * k, 1);
+      tma_bar_init(empty0 + 8 * k, IV_GROUP);        // one arrival per warp
     }
+    for (int k = 0; k < IV_PSLOTS; ++k) tma_bar_init(pfull0 + 8 * k, IV_GROUP);
     tma_bar_init_fence();
   }
-  // row of this warp: audio chunk * 8 + w at frame index t, -1 = not voiced / beyond the utterance
+  // row owned by this warp for loading, selection and the soft-max: audio chunk * 8 + w at frame index t,
+  // -1 = not voiced / beyond the utterance
   int row = -1;
-  if (w < IV_GROUP) {
+  {
     const int b = chunk * IV_GROUP + w;
     if (b < B) {
       const int f0 = frame_off[b];
@@ -280,37 +312,44 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
       }
     }
   }
-  if (threadIdx.x < 128) s_bitmap[threadIdx.x] = 0u;
+  if (threadIdx.x < 128) sm.bitmap[threadIdx.x] = 0u;
+  for (int i = threadIdx.x; i < IV_GROUP * IV_NSEL * 2; i += blockDim.x) (&sm.pos[0][0])[i] = 0xFFFFFFFFu;
   const int sel = (row >= 0 && lane < IV_NSEL) ? gsel[(size_t)row * IV_NSEL + lane] : -1;
-  if (w < IV_GROUP)
-    for (int d = lane; d < FB_DIM; d += 32) s_x[w][d] = (row >= 0) ? feats[(size_t)row * FB_DIM + d] : 0.f;
+  for (int d = lane; d < FB_DIM; d += 32) sm.x[w][d] = (row >= 0) ? feats[(size_t)row * FB_DIM + d] : 0.f;
   __syncthreads();
-  if (sel >= 0) atomicOr(&s_bitmap[sel >> 5], 1u << (sel & 31));
-  // this row's multipliers, in the lane's registers as PAIRS: entries e = 2 lane + 64 m and e + 1, so a component costs one
-  // 64-bit shared-memory load and one packed FFMA2 per two entries.  Entry e < IV_PACKED: x_r x_c (halved on the diagonal)
-  // against the packed inverse covariance; entry IV_PACKED + d: -x_d against mean x inverse covariance, so that one pass
-  // over the staged block yields q - lin
-  float2 xx[IV_XX_PAIRS];
+  if (sel >= 0) atomicOr(&sm.bitmap[sel >> 5], 1u << (sel & 31));
+  // the multipliers of this warp's four rows for its entry slice: pair p = es * IV_SLICE_PAIRS + lane + 32 m
+  float2 xx[IV_RPG][IV_LP];
 #pragma unroll
-  for (int m = 0; m < IV_XX_PAIRS; ++m) {
-    const int e = 2 * lane + 64 * m;
-    float2 v = make_float2(0.f, 0.f);
-    if (e < IV_PACKED) {                              // IV_PACKED is even: a pair is on one side as a whole
+  for (int m = 0; m < IV_LP; ++m) {
+    const int lp = lane + 32 * m, pr = es * IV_SLICE_PAIRS + lp;
+    const bool valid = lp < IV_SLICE_PAIRS && pr < IV_PAIRS;
+    const int e = 2 * pr;
+    int r0 = 0, c0 = 0, r1 = 0, c1 = 0;
+    const bool quad = valid && e < IV_PACKED;        // IV_PACKED is even: a pair is on one side as a whole
+    if (quad) {
       const unsigned short rc0 = rc_table[e], rc1 = rc_table[e + 1];
-      const int r0 = rc0 >> 8, c0 = rc0 & 255, r1 = rc1 >> 8, c1 = rc1 & 255;
-      const float p0 = s_x[w][r0] * s_x[w][c0], p1 = s_x[w][r1] * s_x[w][c1];
-      v = make_float2((r0 == c0) ? 0.5f * p0 : p0, (r1 == c1) ? 0.5f * p1 : p1);
-    } else if (e < IV_ENT) {
-      v = make_float2(-s_x[w][e - IV_PACKED], -s_x[w][e + 1 - IV_PACKED]);
+      r0 = rc0 >> 8; c0 = rc0 & 255; r1 = rc1 >> 8; c1 = rc1 & 255;
     }
-    xx[m] = v;
+#pragma unroll
+    for (int k = 0; k < IV_RPG; ++k) {
+      const float *xr = sm.x[rg * IV_RPG + k];
+      float2 v = make_float2(0.f, 0.f);
+      if (quad) {
+        const float p0 = xr[r0] * xr[c0], p1 = xr[r1] * xr[c1];
+        v = make_float2((r0 == c0) ? 0.5f * p0 : p0, (r1 == c1) ? 0.5f * p1 : p1);
+      } else if (valid) {
+        v = make_float2(-xr[e - IV_PACKED], -xr[e + 1 - IV_PACKED]);
+      }
+      xx[k][m] = v;
+    }
   }
   __syncthreads();
   if (w == 0) {                                       // ordered list of the components any row of the CTA selected
     const int nw = (C + 31) >> 5;                     // bitmap words, 4 per lane
     int cnt = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cnt += (lane * 4 + k < nw) ? __popc(s_bitmap[lane * 4 + k]) : 0;
+    for (int k = 0; k < 4; ++k) cnt += (lane * 4 + k < nw) ? __popc(sm.bitmap[lane * 4 + k]) : 0;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -320,69 +359,98 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
     int pos = incl - cnt;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      sm.prefix[lane * 4 + k] = (unsigned short)pos;
       if (lane * 4 + k < nw) {
-        unsigned bits = s_bitmap[lane * 4 + k];
+        unsigned bits = sm.bitmap[lane * 4 + k];
         while (bits) {
           const int bpos = __ffs(bits) - 1;
           bits &= bits - 1;
-          s_list[pos++] = (lane * 4 + k) * 32 + bpos;
+          sm.list[pos++] = (lane * 4 + k) * 32 + bpos;
         }
       }
     }
-    if (lane == 31) s_n = incl;
+    if (lane == 31) sm.n = incl;
   }
   __syncthreads();
-  const int n_union = s_n;
+  const int n_union = sm.n;
   if (n_union == 0) return;
-  for (int i = threadIdx.x; i < n_union; i += blockDim.x) s_gc[i] = gconsts[s_list[i]];      // not a global load per loop trip
+  for (int i = threadIdx.x; i < n_union; i += blockDim.x) sm.gc[i] = gconsts[sm.list[i]];      // not a global load per loop trip
+  if (sel >= 0) {                                     // where in the union is my selection, and which of my 20 is it
+    const int ui = sm.prefix[sel >> 5] + __popc(sm.bitmap[sel >> 5] & ((1u << (sel & 31)) - 1u));
+    reinterpret_cast<unsigned char *>(&sm.pos[ui][0])[w] = (unsigned char)lane;
+  }
+  if (lane < IV_NSEL) sm.ll[w][lane] = -INFINITY;
   __syncthreads();
-  // Staging: thread 0 streams the union's components through the ring with two bulk copies each (packed inverse
-  // covariance, 10.5 KB, and mean x inverse covariance, 288 B) that complete on the slot's "full" mbarrier; every warp
-  // waits for it -- also the warps whose row did not select the component, which keeps all of them within one ring round
-  // -- and releases the slot on its "empty" mbarrier.  No CTA-wide barrier and no per-thread staging instructions (the
-  // cp.async version spent more issue slots on staging and __syncthreads than on the quadratic forms: ncu 190 M
-  // instructions for ~50 M of arithmetic).  A separate producer warp was measured slower: 9 warps of 110 registers do not
-  // fit twice into the SM's four register files, and one CTA per SM cannot hide the L2 round trips.
-  const uint32_t full0 = tma_smem_u32(s_bar), empty0 = tma_smem_u32(s_bar + IV_POST_STAGES);
   auto issue = [&](int ui) {
     if (ui >= n_union) return;
     const int slot = ui % IV_POST_STAGES, round = ui / IV_POST_STAGES;
     if (round > 0) tma_bar_wait(empty0 + 8 * slot, (round - 1) & 1);
-    const int c = s_list[ui];
+    const int c = sm.list[ui];
     tma_bar_expect_tx(full0 + 8 * slot, IV_ENT * 4);
-    tma_bulk_g2s(tma_smem_u32(s_S[slot]), inv_covars_packed + (size_t)c * IV_PACKED, IV_PACKED * 4, full0 + 8 * slot);
-    tma_bulk_g2s(tma_smem_u32(s_S[slot] + IV_PACKED), means_invcovars + (size_t)c * FB_DIM, FB_DIM * 4, full0 + 8 * slot);
+    tma_bulk_g2s(tma_smem_u32(sm.S[slot]), inv_covars_packed + (size_t)c * IV_PACKED, IV_PACKED * 4, full0 + 8 * slot);
+    tma_bulk_g2s(tma_smem_u32(sm.S[slot] + IV_PACKED), means_invcovars + (size_t)c * FB_DIM, FB_DIM * 4, full0 + 8 * slot);
+  };
+  // the four slice partials of (row r, union member uc) -> log-likelihood, in slice order
+  auto combine = [&](int uc) {
+    const int ps = uc % IV_PSLOTS;
+    tma_bar_wait(pfull0 + 8 * ps, (uc / IV_PSLOTS) & 1);
+    if (lane < IV_GROUP) {
+      const unsigned p = reinterpret_cast<const unsigned char *>(&sm.pos[uc][0])[lane];
+      if (p != 0xFFu) {
+        const int g = lane / IV_RPG, k = lane % IV_RPG;
+        const float q = ((sm.part[ps][g][0][k] + sm.part[ps][g][1][k]) + sm.part[ps][g][2][k]) + sm.part[ps][g][3][k];
+        sm.ll[lane][p] = sm.gc[uc] - q;               // gconst + lin - q
+      }
+    }
   };
   if (threadIdx.x == 0)
     for (int u0 = 0; u0 < IV_POST_STAGES - 1; ++u0) issue(u0);
-  float my_ll = -INFINITY;
   for (int ui = 0; ui < n_union; ++ui) {
     const int slot = ui % IV_POST_STAGES;
-    const int c = s_list[ui];
-    const int pos = __ffs(__ballot_sync(0xffffffffu, sel == c)) - 1;
+    const bool need = sm.pos[ui][rg] != 0xFFFFFFFFu;  // some row of my group selected it
     if (threadIdx.x == 0) issue(ui + IV_POST_STAGES - 1);            // into the slot component ui - 1 used
     tma_bar_wait(full0 + 8 * slot, (ui / IV_POST_STAGES) & 1);
-    if (pos >= 0) {
-      const float *S = s_S[slot];
-      const float2 *S2 = reinterpret_cast<const float2 *>(S) + lane;
-      float2 q2 = make_float2(0.f, 0.f), q3 = make_float2(0.f, 0.f);      // two chains: FFMA2 latency
+    if (need) {
+      const float2 *S2 = reinterpret_cast<const float2 *>(sm.S[slot]) + es * IV_SLICE_PAIRS + lane;
+      float2 acc[IV_RPG];
 #pragma unroll
-      for (int m = 0; m < IV_XX_PAIRS; ++m) {
-        // only the last pair index is partly outside the block (xx is zero there, but the buffer holds no defined value)
-        if (64 * m + 63 < IV_ENT || 2 * lane + 64 * m < IV_ENT) {
-          if (m & 1) q3 = __ffma2_rn(S2[32 * m], xx[m], q3);
-          else q2 = __ffma2_rn(S2[32 * m], xx[m], q2);
+      for (int k = 0; k < IV_RPG; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < IV_LP; ++m) {
+        // only the last pair index is partly outside the slice (xx is zero there, but the buffer holds no defined value)
+        const bool inside = 32 * m + 31 < IV_SLICE_PAIRS && (IV_ES - 1) * IV_SLICE_PAIRS + 32 * m + 31 < IV_PAIRS;
+        if (inside || (lane + 32 * m < IV_SLICE_PAIRS && es * IV_SLICE_PAIRS + lane + 32 * m < IV_PAIRS)) {
+          const float2 s2 = S2[32 * m];
+#pragma unroll
+          for (int k = 0; k < IV_RPG; ++k) acc[k] = __ffma2_rn(s2, xx[k][m], acc[k]);
         }
       }
-      float tot = -((q2.x + q3.x) + (q2.y + q3.y));    // lin - q
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-      if (lane == pos) my_ll = s_gc[ui] + tot;
+      // 4 rows x 32 lanes -> one total per row: exchange halves (rows 0,1 | 2,3), then (row a | row b), then a butterfly
+      const float t0 = acc[0].x + acc[0].y, t1 = acc[1].x + acc[1].y, t2 = acc[2].x + acc[2].y, t3 = acc[3].x + acc[3].y;
+      const bool hi = (lane & 16) != 0;
+      float k0 = hi ? t2 : t0, k1 = hi ? t3 : t1;
+      k0 += __shfl_xor_sync(0xffffffffu, hi ? t0 : t2, 16);
+      k1 += __shfl_xor_sync(0xffffffffu, hi ? t1 : t3, 16);
+      const bool b8 = (lane & 8) != 0;
+      float kk = b8 ? k1 : k0;
+      kk += __shfl_xor_sync(0xffffffffu, b8 ? k0 : k1, 8);
+      kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+      kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+      kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+      if ((lane & 7) == 0) sm.part[ui % IV_PSLOTS][rg][es][(hi ? 2 : 0) + (b8 ? 1 : 0)] = kk;
     }
+    if (ui >= IV_COMB_LAG && ((ui - IV_COMB_LAG) % IV_GROUP) == w) combine(ui - IV_COMB_LAG);
     __syncwarp();
-    if (lane == 0) tma_bar_arrive(empty0 + 8 * slot);
+    if (lane == 0) {
+      tma_bar_arrive(pfull0 + 8 * (ui % IV_PSLOTS));
+      tma_bar_arrive(empty0 + 8 * slot);
+    }
   }
+  for (int uc = max(0, n_union - IV_COMB_LAG); uc < n_union; ++uc)
+    if ((uc % IV_GROUP) == w) combine(uc);
+  __syncthreads();
   if (row < 0) return;
+  const float my_ll = (lane < IV_NSEL) ? sm.ll[w][lane] : -INFINITY;
   // softmax / pruning, exactly as in fgmm_post_kernel
   float m = my_ll;
 #pragma unroll
@@ -392,6 +460,7 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
   for (int j = 0; j < IV_NSEL; ++j) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, e, j));
   float p = e * (float)(1.0 / (double)sum);
   if (min_post != 0.f) {
+    // argmax (first maximum), prune, renormalise (fgmm-global-gselect-to-post.cc)
     float bv = (lane < IV_NSEL) ? p : -1.f;
     int bl = lane;
 #pragma unroll
@@ -740,7 +809,7 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
 // memory and feed the FP64 pipe; the gammas of the next 64 components are prefetched into registers during the current
 // 64.  Grid (b-chunks, column blocks): the CTAs of one column block run side by side, so its rows come from HBM once and
 // from L2 for the other utterance chunks.  Arithmetic and summation order per entry are those of the kernel above.
-#define IV_QUAD_STAGES 6
+#define IV_QUAD_STAGES 12
 #define IV_QUAD_STAGE_COMPS 4
 #define IV_QUAD_COLS 256
 #define IV_QUAD_RING_BYTES (IV_QUAD_STAGES * IV_QUAD_STAGE_COMPS * IV_QUAD_COLS * 4)
@@ -965,8 +1034,8 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
       s_l11[ib][jb] = 0.0;
       __syncthreads();
       bool ok = true;
-#pragma unroll 1
       IV_LAP(11);
+#pragma unroll 1
       for (int kb = 0; kb < IV_NB; kb += 8) {
         if (warp == 0) {
           double d[8][8];                                // lower triangle of the sub-block, the same in every lane
@@ -1533,7 +1602,11 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
                                                                     done_flag);
   } else {
     const int n_chunks = fb_div_up(B, IV_GROUP);
-    fgmm_post_group_kernel<<<ctx->max_frames * n_chunks, 256, 0, ctx->stream>>>(
+    static std::atomic<unsigned long long> attr_post_mask{0};
+    if (fb_once_per_device(attr_post_mask, ctx->device)) {
+      FB_CUDA(cudaFuncSetAttribute(fgmm_post_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostSmem)));
+    }
+    fgmm_post_group_kernel<<<ctx->max_frames * n_chunks, 256, sizeof(PostSmem), ctx->stream>>>(
         ctx->feats_f32.p, v->gsel.p, v->gconsts.p, v->means_invcovars.p, v->inv_covars.p, v->rc_table.p, ctx->frame_off.p,
         ctx->vrank.p, ctx->row_off.p, B, v->C, n_chunks, v->min_post, v->post.p, done_flag);
   }
