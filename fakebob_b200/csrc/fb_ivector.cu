@@ -952,8 +952,11 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   long long st[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long st_t = clock64();
 #define IV_LAP(i) do { const long long n_ = clock64(); st[i] += n_ - st_t; st_t = n_; } while (0)
+  long long st2[4] = {0, 0, 0, 0};
+#define IV_LAP2(i) do { const long long n_ = clock64(); st2[i] += n_ - st_t; st_t = n_; } while (0)
 #else
 #define IV_LAP(i)
+#define IV_LAP2(i)
 #endif
   extern __shared__ double s_dyn[];
   double *rhs = s_dyn;                               // [R]   right-hand side -> y -> w
@@ -1049,6 +1052,7 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
 #pragma unroll
           for (int c = 0; c < 8; ++c) x[c] = has_row ? s_a[xi][kb + c] : 0.0;
           double dinv[8];
+          IV_LAP2(0);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             if (!(d[c][c] > 0.0)) ok = false;
@@ -1065,25 +1069,22 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
 #pragma unroll
             for (int c2 = c + 1; c2 < 8; ++c2) x[c2] = fma(-x[c], d[c2][c], x[c2]);
           }
-          // publish: lane r < 8 writes row r of the factored sub-block, every lane its solved row
+          IV_LAP2(1);
+          // publish the factored sub-block: every lane holds the same values, lane 0 stores them in one straight run
+          // ("lane r writes row r" took 2 k cycles per sub-block in 8 serialised branches, all lanes storing the same
+          // value to the same address 0.8 k); then every lane its solved row
+          if (lane == 0)
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (lane == r) {
+          for (int r = 0; r < 8; ++r) {
 #pragma unroll
-              for (int c = 0; c <= r; ++c) {
-                s_l11[kb + r][kb + c] = d[r][c];
-                if (kb + r < nbk) panel[(kb + r) * IV_PSTRIDE + kb + c] = d[r][c];
-              }
-              s_invd[kb + r] = dinv[r];
-              if (kb + r < nbk) invd[k0 + kb + r] = dinv[r];
-            }
+            for (int c = 0; c <= r; ++c) s_l11[kb + r][kb + c] = d[r][c];
+            s_invd[kb + r] = dinv[r];
+          }
           if (has_row) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              s_l11[xi][kb + c] = x[c];
-              if (xi < nbk) panel[xi * IV_PSTRIDE + kb + c] = x[c];
-            }
+            for (int c = 0; c < 8; ++c) s_l11[xi][kb + c] = x[c];
           }
+          IV_LAP2(2);
         }
         __syncthreads();
         IV_LAP(2);
@@ -1103,8 +1104,17 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
         IV_LAP(11);
       }
       if (!ok && tid == 0) s_fail = 1;
-      s_l11t[ja][ia] = s_l11[ia][ja] * s_invd[ia];
-      s_l11t[jb][ib] = s_l11[ib][jb] * s_invd[ib];
+      // all threads: the factor into the panel (it is written back to A from there), 1 / diagonal for the back substitution,
+      // and the pre-scaled transposed copy for the panel solve -- kept out of warp 0's serial section (a lone warp gets one
+      // shared-memory instruction through per ~9 cycles)
+      auto finish = [&](int i, int j) {
+        const double l = s_l11[i][j];
+        s_l11t[j][i] = l * s_invd[i];
+        if (i < nbk && j <= i) panel[i * IV_PSTRIDE + j] = l;
+      };
+      finish(ia, ja);
+      finish(ib, jb);
+      if (tid < nbk) invd[k0 + tid] = s_invd[tid];
     }
     __syncthreads();
     IV_LAP(2);
@@ -1257,6 +1267,7 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   if (b == 0 && (tid == 0 || tid == 511))
     printf("solve tid %d clk: init %lld load %lld diag %lld l21 %lld rhs+wb %lld trailing: setup %lld fma %lld rmw %lld rest %lld sync %lld; backsub %lld; diag init+update %lld\n",
            tid, st[0], st[1], st[2], st[3], st[4], st[7], st[8], st[9], st[5], st[10], st[6], st[11]);
+  if (b == 0 && tid == 0) printf("solve warp 0 diag: loads %lld factor %lld publish %lld\n", st2[0], st2[1], st2[2]);
 #endif
   if (crank == 0)
     for (int r = tid; r < R; r += nt) ivec[(size_t)b * R + r] = (float)(rhs[r] - ((r == 0) ? prior_offset : 0.0));
