@@ -941,6 +941,7 @@ ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gam
 // ------------------------------------------------------------------------------------------------
 #define IV_NB 32
 #define IV_PSTRIDE 33      // padded panel row stride (doubles): consecutive rows map to different banks
+#define IV_SDIAG (IV_NB * (IV_NB - 1) / 2)          // strict lower triangle of a diagonal block
 #define IV_SOLVE_CLUSTER 2 // CTAs (SMs) per utterance: at B = 51 one CTA per utterance would leave 97 of 148 SMs idle
 
 __global__ void __launch_bounds__(512)
@@ -962,6 +963,8 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   double *rhs = s_dyn;                               // [R]   right-hand side -> y -> w
   double *invd = s_dyn + R;                          // [R]   1 / L[k][k]
   double *panel = s_dyn + 2 * R;                     // [R + 2][IV_PSTRIDE]: rows k0..R-1 of the block column, the rhs row, a zero row
+  double *sdiag = panel + (size_t)(R + 2) * IV_PSTRIDE;   // [blocks][496]: strict lower triangles of the factored diagonal blocks,
+                                                     // entry (k, l) times 1 / L[l][l], kept for the back substitution
   __shared__ double s_l11[IV_NB][IV_PSTRIDE];        // factored diagonal block, identity-padded to 32 x 32
   __shared__ double s_a[IV_NB][IV_PSTRIDE];          // working copy during its factorisation
   __shared__ __align__(16) double s_l11t[IV_NB][IV_NB + 2];   // [q][j] = L[j][q] / L[j][j]: one FMA per substitution step, read in pairs
@@ -1006,12 +1009,19 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
         panel[i * IV_PSTRIDE + j] = use ? v + ((i == j) ? 1.0 : 0.0) : 0.0;
       }
     } else {
-#pragma unroll 13
-      for (int idx = tid; idx < rows * IV_NB; idx += nt) {
-        const int i = idx >> 5, j = idx & 31;
-        const bool use = j < nbk && j <= i;
-        const double v = A[(size_t)(k0 + i) * R + k0 + (j < nbk ? j : 0)];
-        panel[i * IV_PSTRIDE + j] = use ? v : 0.0;
+      // all of a thread's loads in one batch (rows / 16 <= 24 of them for R <= 400): one L2 round trip per block column
+      for (int base = tid; base < rows * IV_NB; base += 24 * nt) {
+        double v[24];
+#pragma unroll
+        for (int u = 0; u < 24; ++u) {
+          const int idx = base + u * nt, i = idx >> 5, j = idx & 31;
+          v[u] = (idx < rows * IV_NB) ? __ldcg(A + (size_t)(k0 + i) * R + k0 + (j < nbk ? j : 0)) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 24; ++u) {
+          const int idx = base + u * nt, i = idx >> 5, j = idx & 31;
+          if (idx < rows * IV_NB) panel[i * IV_PSTRIDE + j] = (j < nbk && j <= i) ? v[u] : 0.0;
+        }
       }
     }
     if (tid < 2 * IV_NB) {
@@ -1111,6 +1121,7 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
         const double l = s_l11[i][j];
         s_l11t[j][i] = l * s_invd[i];
         if (i < nbk && j <= i) panel[i * IV_PSTRIDE + j] = l;
+        if (j < i) sdiag[(size_t)(k0 / IV_NB) * IV_SDIAG + i * (i - 1) / 2 + j] = l * s_invd[j];
       };
       finish(ia, ja);
       finish(ib, jb);
@@ -1166,57 +1177,81 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
         if (j < nbk && j <= i) A[(size_t)(k0 + i) * R + k0 + j] = panel[i * IV_PSTRIDE + j];
       }
     IV_LAP(4);
-    // ---- trailing update A22 -= L21 L21^T on the lower triangle: warp tiles of 8 rows x 128 columns
+    // ---- trailing update A22 -= L21 L21^T on the lower triangle, on the FP64 tensor-core path (mma.sync m8n8k4: one
+    // instruction = 256 FMAs of a warp; 18.6 T FMA/s measured, scripts/fp64_probe.cu): warp tiles of 16 rows x 32 columns =
+    // 2 x 4 fragments, A fragment = 8 rows x 4 panel columns of -L21, B fragment = the same of the column block's rows.
+    // Against the earlier DFMA tiles (8 x 128, 32 accumulators per lane) this takes 8x fewer FP64 instructions and 4x
+    // fewer shared-memory loads per FMA, wastes less on the diagonal (tiles are smaller: 92 % useful instead of 73 %) and
+    // needs only 16 accumulators, so the old values of the NEXT tile are prefetched from L2 during the current one.
     const int rem = rows - nbk;
     if (rem > 0) {
-      const int nrb = (rem + 7) >> 3, ncb = (rem + 127) >> 7;
+      const int nrb = (rem + 15) >> 4, ncb = (rem + 31) >> 5;
       int n_items = 0;
-      for (int cb = 0; cb < ncb; ++cb) n_items += nrb - 16 * cb;
-      for (int it = warp * csize + crank; it < n_items; it += nw * csize) {
+      for (int cb = 0; cb < ncb; ++cb) n_items += max(nrb - 2 * cb, 0);
+      const int g = lane >> 2, tq = lane & 3;
+      auto coords = [&](int it, int &i0, int &j0) {
         int cb = 0, rb = it;
-        while (rb >= nrb - 16 * cb) { rb -= nrb - 16 * cb; ++cb; }
-        rb += 16 * cb;
-        const int i0 = nbk + 8 * rb, j0 = nbk + 128 * cb;          // panel-local rows
-        int ri[8], rj[4];
+        while (rb >= nrb - 2 * cb) { rb -= nrb - 2 * cb; ++cb; }
+        rb += 2 * cb;
+        i0 = nbk + 16 * rb;                            // panel-local rows
+        j0 = nbk + 32 * cb;
+      };
+      // C fragment of tile (mt, nt): row i0 + 8 mt + g, columns j0 + 8 nt + 2 tq + {0, 1}
+      auto load_old = [&](int i0, int j0, double (&o)[2][4][2]) {
 #pragma unroll
-        for (int x = 0; x < 8; ++x) ri[x] = ((i0 + x < rows) ? i0 + x : zrow) * IV_PSTRIDE;
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int y = 0; y < 4; ++y) rj[y] = ((j0 + lane + 32 * y < rows) ? j0 + lane + 32 * y : zrow) * IV_PSTRIDE;
-        // c starts as the old trailing values (their 32 L2 loads are in flight together and overlap the first panel reads;
-        // loaded after the products they cost a second, exposed, round trip per tile) and the products are subtracted
-        double c[8][4];
+          for (int nt2 = 0; nt2 < 4; ++nt2)
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) {
-            const int li = i0 + x, lj = j0 + lane + 32 * y;
-            double old = 0.0;
-            if (li < rows && lj <= li)
-              old = (k0 == 0) ? __ldg(qb + (size_t)li * (li + 1) / 2 + lj) + ((li == lj) ? 1.0 : 0.0)
+            for (int h = 0; h < 2; ++h) {
+              const int li = i0 + 8 * mt + g, lj = j0 + 8 * nt2 + 2 * tq + h;
+              double v = 0.0;
+              if (li < rows && lj <= li)
+                v = (k0 == 0) ? __ldg(qb + (size_t)li * (li + 1) / 2 + lj) + ((li == lj) ? 1.0 : 0.0)
                               : __ldcg(A + (size_t)(k0 + li) * R + k0 + lj);
-            c[x][y] = old;
-          }
-        IV_LAP(7);
-#pragma unroll 8
-        for (int q = 0; q < IV_NB; ++q) {
-          double av[8], bv[4];
+              o[mt][nt2][h] = v;
+            }
+      };
+      const int stride_it = nw * csize;
+      IV_LAP(7);
+      for (int it = warp * csize + crank; it < n_items; it += stride_it) {
+        int i0, j0;
+        coords(it, i0, j0);
+        double cur[2][4][2], old[2][4][2];           // products accumulate from zero: the old values (an L2 round trip) are
+        load_old(i0, j0, old);                       // only needed after the 64 MMAs
 #pragma unroll
-          for (int x = 0; x < 8; ++x) av[x] = panel[ri[x] + q];
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int y = 0; y < 4; ++y) bv[y] = panel[rj[y] + q];
+          for (int nt2 = 0; nt2 < 4; ++nt2) cur[mt][nt2][0] = cur[mt][nt2][1] = 0.0;
+        int ra[2], rb4[4];
 #pragma unroll
-          for (int x = 0; x < 8; ++x)
+        for (int mt = 0; mt < 2; ++mt) ra[mt] = ((i0 + 8 * mt + g < rows) ? i0 + 8 * mt + g : zrow) * IV_PSTRIDE + tq;
 #pragma unroll
-            for (int y = 0; y < 4; ++y) c[x][y] = fma(-av[x], bv[y], c[x][y]);
+        for (int nt2 = 0; nt2 < 4; ++nt2) rb4[nt2] = ((j0 + 8 * nt2 + g < rows) ? j0 + 8 * nt2 + g : zrow) * IV_PSTRIDE + tq;
+#pragma unroll
+        for (int ks = 0; ks < IV_NB / 4; ++ks) {
+          double af[2], bf[4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) af[mt] = -panel[ra[mt] + 4 * ks];
+#pragma unroll
+          for (int nt2 = 0; nt2 < 4; ++nt2) bf[nt2] = panel[rb4[nt2] + 4 * ks];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt2 = 0; nt2 < 4; ++nt2)
+              asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(cur[mt][nt2][0]), "+d"(cur[mt][nt2][1]) : "d"(af[mt]), "d"(bf[nt2]));
         }
         IV_LAP(8);
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int y = 0; y < 4; ++y) {
-            const int li = i0 + x, lj = j0 + lane + 32 * y;
-            if (li < rows && lj <= li) A[(size_t)(k0 + li) * R + k0 + lj] = c[x][y];
-          }
+          for (int nt2 = 0; nt2 < 4; ++nt2)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int li = i0 + 8 * mt + g, lj = j0 + 8 * nt2 + 2 * tq + h;
+              if (li < rows && lj <= li) A[(size_t)(k0 + li) * R + k0 + lj] = old[mt][nt2][h] + cur[mt][nt2][h];
+            }
         IV_LAP(9);
       }
     }
@@ -1230,16 +1265,21 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
   for (int bi = n_blocks - 1; bi >= 0; --bi) {
     const int k0 = bi * IV_NB;
     const int nbk = min(IV_NB, R - k0);
-    if (warp == 0) {
-      double wv = (lane < nbk) ? rhs[k0 + lane] : 0.0;
+    // the update of the rows above needs 32 values of L per row from L2: in flight while warp 0 runs the block's chain
+    const int iu = tid - 32;
+    const bool upd = tid >= 32 && iu < k0;
+    double a[IV_NB];
+    if (warp != 0) {
+#pragma unroll
+      for (int j = 0; j < IV_NB; ++j) a[j] = (upd && j < nbk) ? __ldcg(A + (size_t)(k0 + j) * R + iu) : 0.0;
+    } else {
+      // w_lane = y_lane / L_ll - sum_k (L[k][lane] / L_ll) w_k: the column comes pre-scaled from shared memory (sdiag), so a
+      // step is one shuffle + one FMA and the block starts without an L2 round trip
+      const double *sd = sdiag + (size_t)bi * IV_SDIAG;
       double lcol[IV_NB];                              // column `lane` of the diagonal block
 #pragma unroll
-      for (int k = 0; k < IV_NB; ++k) lcol[k] = (k < nbk && lane < k) ? A[(size_t)(k0 + k) * R + k0 + lane] : 0.0;
-      const double my_inv = (lane < nbk) ? invd[k0 + lane] : 1.0;
-      // w_lane = y_lane / L_ll - sum_k (L[k][lane] / L_ll) w_k: with the column pre-scaled a step is one shuffle + one FMA
-      wv *= my_inv;
-#pragma unroll
-      for (int k = 0; k < IV_NB; ++k) lcol[k] *= my_inv;
+      for (int k = 0; k < IV_NB; ++k) lcol[k] = (lane < k) ? sd[k * (k - 1) / 2 + lane] : 0.0;
+      double wv = (lane < nbk) ? rhs[k0 + lane] * invd[k0 + lane] : 0.0;
 #pragma unroll
       for (int k = IV_NB - 1; k >= 0; --k) {
         if (k < nbk) {
@@ -1249,16 +1289,15 @@ ivec_solve_kernel(const double *__restrict__ quad, const double *__restrict__ li
       }
       if (lane < nbk) rhs[k0 + lane] = wv;
       s_blk[lane] = (lane < nbk) ? wv : 0.0;
+#pragma unroll
+      for (int j = 0; j < IV_NB; ++j) a[j] = 0.0;
     }
     __syncthreads();
-    for (int i = tid; i < k0; i += nt) {
-      double a[IV_NB];                                 // the block's 32 loads in flight together
-#pragma unroll
-      for (int j = 0; j < IV_NB; ++j) a[j] = (j < nbk) ? __ldcg(A + (size_t)(k0 + j) * R + i) : 0.0;
-      double v = rhs[i];
+    if (upd) {
+      double v = rhs[iu];
 #pragma unroll
       for (int j = 0; j < IV_NB; ++j) v -= a[j] * s_blk[j];
-      rhs[i] = v;
+      rhs[iu] = v;
     }
     __syncthreads();
   }
@@ -1660,7 +1699,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   }
   fb_prof_mark(ctx, 12);
   nv.next("fb:ivec_solve");
-  const size_t smem_solve = (2 * (size_t)v->R + ((size_t)v->R + 2) * IV_PSTRIDE) * sizeof(double);
+  const size_t smem_solve = (2 * (size_t)v->R + ((size_t)v->R + 2) * IV_PSTRIDE + (size_t)fb_div_up(v->R, IV_NB) * IV_SDIAG) * sizeof(double);
   static std::atomic<unsigned long long> attr_solve_mask{0};
   if (fb_once_per_device(attr_solve_mask, ctx->device)) {
     FB_CUDA(cudaFuncSetAttribute(ivec_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
