@@ -340,6 +340,9 @@ def load_traffic(kernel):
     return (e["dram_bytes_per_launch"], e["capture"]) if e else (None, None)
 
 
+FP64_TFMA_PEAK = 17.1     # T FMA/s, DFMA, measured on this pool's B200 (DMMA m8n8k4: 18.6)
+
+
 def rooflines(name, prof, rows, n_models, peaks, active_frac=None, b_local=None):
     """Per-kernel algorithmic work / measured stage time -> fraction of the governing measured peak.
     `rows` = voiced rows this rank scores per iteration.  The tensor-pipe kernels are timed inside a millisecond-scale window,
@@ -369,13 +372,21 @@ def rooflines(name, prof, rows, n_models, peaks, active_frac=None, b_local=None)
         af = active_frac if active_frac else 1.0
         mem("ivec_lin", 4.0 * N_MIX * 72 * IV_R * af, "ivec_lin_kernel",
             "bytes = active components x 72 x R x 4 (fp32 Sigma^-1 M rows of the components with gamma != 0; %.0f %% active)" % (100 * af))
-        mem("ivec_quad", 4.0 * N_MIX * (IV_R * (IV_R + 1) // 2) * af, "ivec_quad_kernel",
+        mem("ivec_quad", 4.0 * N_MIX * (IV_R * (IV_R + 1) // 2) * af, "ivec_quad_tma_kernel",
             "bytes = active components x R(R+1)/2 x 4 (fp32 U rows of the components with gamma != 0; %.0f %% active)" % (100 * af))
         tensor("fgmm_post", 2.0 * rows * 20 * (72 * 73 // 2 + 72), "fgmm_post_group_kernel",
                "20 full-covariance log-likelihoods per frame, 2*rows*20*(D(D+1)/2+D) FLOP; CUDA-core kernel, tensor peak shown for scale")
         mem("ivec_solve", 8.0 * B * (IV_R * (IV_R + 1) // 2) + 8.0 * B * IV_R * 2, "ivec_solve_kernel",
             "latency-bound blocked Cholesky in float64 (B*R^3/3 = %.2f GFLOP); bytes = packed posterior precision read + lin + solution" % (B * IV_R ** 3 / 3e9))
         mem("gselect", 4.0 * rows * N_MIX, "gselect_kernel", "bytes = component log-likelihoods read (rows x C x 4)")
+        # the three float64 kernels against the measured FP64 FMA rate (scripts/fp64_probe.cu, profiles/r02_fp64_probe.txt)
+        n_act = N_MIX * af
+        for stage, fmas in (("ivec_lin", n_act * 72 * IV_R * B), ("ivec_quad", n_act * (IV_R * (IV_R + 1) // 2) * B),
+                            ("ivec_solve", B * IV_R ** 3 / 6.0)):
+            if stage in out:
+                a = fmas / (ms[stage] * 1e-3) / 1e12
+                out[stage]["fp64"] = {"achieved_tfma_per_s": a, "peak_tfma_per_s": FP64_TFMA_PEAK, "frac": a / FP64_TFMA_PEAK,
+                                      "algorithmic_fma_per_launch": fmas}
     mem("mfcc", 2.0 * B * N_SAMPLES + 4.0 * B * (N_SAMPLES // 160) * 24, "mfcc_kernel", "bytes = int16 wave read + MFCC written (issue-bound kernel)")
     mem("feats", 4.0 * B * (N_SAMPLES // 160) * 24 + 2.0 * rows * 160 * 2, "feats_kernel", "bytes = MFCC read + fp16 hi/lo operand image written")
     return out, ms

@@ -11,7 +11,7 @@
 // which keeps ~22 significant bits per operand (fp32 Kaldi keeps 24).  W is pre-multiplied by
 // log2(e) so the epilogue works in the log2 domain with ex2.approx.
 //
-// Kernel shape (cta_group::1, persistent, 1 CTA / SM, 352 threads).  Measured on B200 (profiles/r01_*, scripts/*_probe.cu):
+// Kernel shape (cta_group::1, persistent, 1 CTA / SM, 608 threads).  Measured on B200 (profiles/r01_*, scripts/*_probe.cu):
 //  * with both operands in shared memory the N=64 MMAs need 192 B/clk of smem reads and run at 48-68 clk instead of 32,
 //    so the A operand lives in TENSOR MEMORY;
 //  * the tensor pipe's issue queue is shallow: every mbarrier wait one thread does between two 15-MMA jobs idles the
@@ -23,15 +23,17 @@
 //            columns, hi+lo; shared-variance mode: 20 KB sub-stages, two per ring entry).  Operand images are stored in
 //            global memory already in the UMMA canonical no-swizzle K-major core-matrix order, so every copy is one
 //            contiguous transfer.
-//   warp 1, warp 10   issuers (one elected lane each) for tile 0 / tile 1: tcgen05.cp moves their tile's A entries
+//   warp 1, warp 2    issuers (one elected lane each) for tile 0 / tile 1: tcgen05.cp moves their tile's A entries
 //            smem -> TMEM (304 columns: 2 tiles x (hi 80 + lo 72)), then per job 15 (shared mode) or 30 tcgen05.mma
 //            M128 N64 K16 with A from TMEM and B from the ring slot.  Jobs are numbered globally (2 * step + tile) and use
 //            accumulator job % 3 (three 64-column accumulators); a ring slot is released by one arrival per issuer.
 //            Barriers between issuers and epilogue are per (accumulator, tile) so that every barrier has one waiter that
 //            sees all of its phases (a parity wait cannot tell phase n from n+2).
-//   warps 2-9 epilogue (4 per tile, TMEM lane quadrant = warp % 4): tcgen05.ld 32x32b.x32, packed FADD2 of the shared x^2
-//            term, online max / sum of ex2 with Kaldi's log(FLT_EPSILON) pruning; gconst is already inside the accumulator
-//            (extra k-block of the hi.hi part: "ones" columns of A times [g_hi g_mid g_lo] rows of W).
+//   warps 3-18 epilogue (8 per tile: TMEM lane quadrant = warp % 4, two warps per quadrant each taking 32 of the 64
+//            accumulator columns): tcgen05.ld 32x32b.x32, online max / sum of ex2 in groups of 8 values (packed FADD2 /
+//            EX2 on the groups that can still contribute) with Kaldi's log(FLT_EPSILON) pruning; gconst is already inside
+//            the accumulator (extra k-block of the hi.hi part: "ones" columns of A times [g_hi g_mid g_lo] rows of W).
+//            The per-slot running (max, sum) live in registers for the reference's slot counts (template kNM = 2 / 5 / 6).
 // Work = the sequence of 64-column stages ordered (super-tile, [model,] stage), cut into 148 equal contiguous ranges; a CTA
 // writes one (max, sum) partial per row and segment (run of its stages inside one super-tile), gmm_frame_kernel recomputes
 // the cut points to merge them.
@@ -42,8 +44,12 @@
 // ll_0 always uses the three-term split; the difference sub-stages use `delta_terms` of the three products
 // (1: hi.hi, 2: hi.hi + hi.lo, 3: all) -- the differences are small, so their fp16 rounding error is small in absolute
 // terms (scripts/gmm_precision_study.py; fb_set_gmm_delta_terms in the header).
-// Tried and rejected (same-clock A/B, cycles per CTA): 16 epilogue warps of 32 columns (+5 %); four accumulators (two per
-// tile, no cross-tile coupling) with the x^2-lo operand kept in shared memory and a 4-slot ring (+7 %).
+// Round-2 measurements (profiles/r02_gmm_variants_ab.txt): with the difference sub-stages the kernel is EPILOGUE bound
+// (123 us vs 72 us with the log-sum-exp compiled out), hence sixteen epilogue warps, slot 0 merged into one accumulator
+// and the packed log-sum-exp: 129 -> ~101-107 us at C2 (tensor pipe 61 % busy).  Tried and not paying (same-box A/B): five
+// accumulators, 4-column LSE groups, suspended (parked) barrier waits for producer / issuers, programmatic dependent
+// launch at S = 50, kNM register-resident slot state (+-0).  In the general (non-shared) mode of round 1: four
+// accumulators with the x^2-lo operand in shared memory and a 4-slot ring (+7 %).
 #include "fb_common.cuh"
 #include <math.h>
 #include <atomic>

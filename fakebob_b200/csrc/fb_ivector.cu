@@ -384,7 +384,7 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
   auto issue = [&](int ui) {
     if (ui >= n_union) return;
     const int slot = ui % IV_POST_STAGES, round = ui / IV_POST_STAGES;
-    if (round > 0) tma_bar_wait(empty0 + 8 * slot, (round - 1) & 1);
+    if (round > 0) { tma_bar_wait(empty0 + 8 * slot, (round - 1) & 1); tma_fence_proxy_async(); }
     const int c = sm.list[ui];
     tma_bar_expect_tx(full0 + 8 * slot, IV_ENT * 4);
     tma_bulk_g2s(tma_smem_u32(sm.S[slot]), inv_covars_packed + (size_t)c * IV_PACKED, IV_PACKED * 4, full0 + 8 * slot);
@@ -850,7 +850,7 @@ ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gam
   auto issue = [&](int st) {
     if (st >= n_stages) return;
     const int slot = st % IV_QUAD_STAGES, round = st / IV_QUAD_STAGES;
-    if (round > 0) tma_bar_wait(empty0 + 8 * slot, (round - 1) & 1);
+    if (round > 0) { tma_bar_wait(empty0 + 8 * slot, (round - 1) & 1); tma_fence_proxy_async(); }
     const int nc = min(IV_QUAD_STAGE_COMPS, n_act - st * IV_QUAD_STAGE_COMPS);
     tma_bar_expect_tx(full0 + 8 * slot, nc * seg_bytes);
     for (int k = 0; k < nc; ++k)

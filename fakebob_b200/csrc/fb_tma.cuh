@@ -26,6 +26,9 @@ __device__ __forceinline__ void tma_bar_wait(uint32_t bar, uint32_t parity) {
         "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
+// Orders this thread's view of earlier generic-proxy accesses to shared memory (the consumers' loads, made visible to it by
+// the "empty" mbarrier) before async-proxy writes it issues afterwards (the bulk copy that refills the slot).
+__device__ __forceinline__ void tma_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // bytes: multiple of 16; dst and src 16-byte aligned
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

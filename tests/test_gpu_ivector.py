@@ -110,3 +110,26 @@ def test_iv_attack_bit_exact_given_same_scores(small_iv_tree, iv_osi, task):
     assert flag_g == flag_o and fb.iters_done == len(ob.log)
     assert np.array_equal(adv_g, adv_o)
     assert np.array_equal(fb.log[:, 1], np.array([float(np.asarray(r[1]).reshape(-1)[0]) for r in ob.log]))
+
+
+def test_ivector_path_is_bitwise_reproducible(iv_osi):
+    """The TMA-staged kernels (posteriors, quad) synchronise generic-proxy reads of bulk-copied shared memory and their
+    partial-sum ring through mbarriers only; the slice partials are combined in a fixed order.  Same batch in -> the same
+    bits out, every time (a timing-dependent hazard would show up as a flipped low bit in some repetition).  The batch
+    mixes near-duplicate audios (shared Gaussian selections, like an NES batch) with unrelated ones."""
+    from fakebob_b200.engine import to_audio_list
+    base = to_audio_list([make_audio(71, 0)])[0]                 # int16
+    rng = np.random.RandomState(5)
+    near = [np.clip(base.astype(np.int32) + rng.randint(-3, 4, size=base.shape), -32768, 32767).astype(np.int16) for _ in range(9)]
+    lst = to_audio_list(near + [make_audio(72, 1, n=24000), make_audio(73, 2, n=40000)])
+    ref = None
+    for rep in range(12):
+        scores, ivs = iv_osi._engine.score_plda(lst, want_ivectors=True)
+        gsel, post = iv_osi._engine.posteriors()
+        cur = (scores.copy(), ivs.copy(), gsel.copy(), post.copy())
+        if ref is None:
+            ref = cur
+            assert np.isfinite(scores).all() and np.isfinite(ivs).all()
+        else:
+            for a, b in zip(ref, cur):
+                assert np.array_equal(a, b), "repetition %d differs" % rep
