@@ -109,8 +109,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 #define MFCC_WARPS 8
-#define FFT_PAD(i) ((i) + ((i) >> 3))          // float2 index padding (one slot per 8): stores of all stages stay <= 3 wavefronts
-#define FFT_BUF 320                             // 256 + 32 padding, rounded up
+// float2 index paddings of the two FFT buffers, chosen per buffer so that EVERY access pattern of the three stages is
+// conflict-free (a warp's 32 float2 = 2 wavefronts; one slot per 8 elements for both buffers cost 3 on five of the seven
+// access groups: ncu counted 42 % of the kernel's shared-memory wavefronts as bank conflicts):
+//   buffer A: stage-A stores (index 8 lane + c), unit-stride loads / stores (lane + 32 r)      -> one slot per 16
+//   buffer B: stage-B stores (index 32 (lane >> 2) + (lane & 3) + 4 r), unit-stride loads      -> four slots per 32
+#define FFT_PAD_A(i) ((i) + ((i) >> 4))
+#define FFT_PAD_B(i) ((i) + 4 * ((i) >> 5))
+#define FFT_BUF 320                             // >= 256 + 32 padding
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -226,7 +232,7 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
     float2 v2 = make_float2(y[2][2 * h], y[2][2 * h + 1]), v3 = make_float2(y[3][2 * h], y[3][2 * h + 1]);
     dft4(v0, v1, v2, v3);
     const int o = 4 * (2 * lane + h);
-    bufA[FFT_PAD(o)] = v0; bufA[FFT_PAD(o + 1)] = v1; bufA[FFT_PAD(o + 2)] = v2; bufA[FFT_PAD(o + 3)] = v3;
+    bufA[FFT_PAD_A(o)] = v0; bufA[FFT_PAD_A(o + 1)] = v1; bufA[FFT_PAD_A(o + 2)] = v2; bufA[FFT_PAD_A(o + 3)] = v3;
   }
   __syncwarp();
   // ---- stage B (radix 8, Ns = 4): butterfly j = lane, k = j & 3, twiddle exp(-2 pi i r k / 32)
@@ -234,25 +240,25 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
     const int k = lane & 3;
     float2 u[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) u[r] = bufA[FFT_PAD(lane + 32 * r)];
+    for (int r = 0; r < 8; ++r) u[r] = bufA[FFT_PAD_A(lane + 32 * r)];
 #pragma unroll
     for (int r = 1; r < 8; ++r) u[r] = cmul(u[r], s_tw[r * k * 16]);
     dft8(u);
     const int j0 = ((lane >> 2) << 5) + k;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) bufB[FFT_PAD(j0 + 4 * r)] = u[r];
+    for (int r = 0; r < 8; ++r) bufB[FFT_PAD_B(j0 + 4 * r)] = u[r];
   }
   __syncwarp();
   // ---- stage C (radix 8, Ns = 32): k = lane, twiddle exp(-2 pi i r k / 256); out[k + 32 r]
   {
     float2 u[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) u[r] = bufB[FFT_PAD(lane + 32 * r)];
+    for (int r = 0; r < 8; ++r) u[r] = bufB[FFT_PAD_B(lane + 32 * r)];
 #pragma unroll
     for (int r = 1; r < 8; ++r) u[r] = cmul(u[r], s_tw[r * lane * 2]);
     dft8(u);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) bufA[FFT_PAD(lane + 32 * r)] = u[r];
+    for (int r = 0; r < 8; ++r) bufA[FFT_PAD_A(lane + 32 * r)] = u[r];
   }
   __syncwarp();
   // ---- real-FFT post-processing -> power spectrum bins 0..255 in bufB viewed as float[256]
@@ -260,8 +266,8 @@ mfcc_kernel(const int16_t *__restrict__ wave, const int64_t *__restrict__ wave_o
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const int k = lane + 32 * m;
-    const float2 zk = bufA[FFT_PAD(k)];
-    float2 zc = bufA[FFT_PAD((256 - k) & 255)];
+    const float2 zk = bufA[FFT_PAD_A(k)];
+    float2 zc = bufA[FFT_PAD_A((256 - k) & 255)];
     zc.y = -zc.y;
     const float2 ev = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
     const float2 df = csub(zk, zc);
