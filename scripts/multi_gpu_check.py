@@ -32,7 +32,7 @@ def main():
     model = gmm_OSI(os.path.join(tempfile.mkdtemp(), "g"), t["models"], t["ubm"], pre_model_dir=t["pre_model_dir"], device=local)
     audio = synth.synth_utterance(41, 1, 32000)
     thr = 1e3                                       # unreachable: every iteration runs (no early stop)
-    hp = dict(max_iter=12, samples_per_draw=16, plateau_length=3)
+    hp = dict(max_iter=int(os.environ.get("MG_ITERS", "12")), samples_per_draw=int(os.environ.get("MG_S", "16")), plateau_length=3)
     single = None
     if rank == 0:
         fb1 = FakeBob("OSI", "untargeted", model, seed=123, verbose=False, **hp)
@@ -67,7 +67,7 @@ def main():
     os.environ.pop("FB_NO_P2P", None)
     # a second, shorter utterance right after (new session number, other buffer sizes), still over peer memory
     audio2 = synth.synth_utterance(42, 2, 16000)
-    fb2 = FakeBob("OSI", "untargeted", model, seed=7, verbose=False, max_iter=6, samples_per_draw=10)
+    fb2 = FakeBob("OSI", "untargeted", model, seed=7, verbose=False, max_iter=6, samples_per_draw=max(10, 2 * world + 2))   # every rank needs a pair
     fb2.attack(audio2, None, threshold=thr)
     advs = [None] * world
     dist.all_gather_object(advs, fb2.final_adver)
