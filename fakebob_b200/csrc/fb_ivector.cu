@@ -639,7 +639,7 @@ ivec_lin_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, 
   const int a_lo = (int)((long long)n_act * split / n_splits), a_hi = (int)((long long)n_act * (split + 1) / n_splits);
   const int ncg = (R + 3) / 4;
   const int ug = threadIdx.x / ncg, cg = threadIdx.x - ug * ncg;      // utterance group 0..3, column group
-  const bool active = ug < 4;
+  const bool active = ug < 4 && ug * 8 < nb;            // utterance groups beyond the batch (B = 51: the last 8 slots) skip the work
   const int r0 = cg * 4;
   double acc[4][8];
 #pragma unroll

@@ -415,6 +415,29 @@ def test_library_contains_sm100a_tensor_core_and_tma_code():
         assert mnemonic in sass, mnemonic
 
 
+def test_library_ivector_kernels_use_tma_and_fp64_tensor_path():
+    """The i-vector kernels of the built library: posteriors and the quadratic-term accumulation stage their operands with
+    TMA bulk copies completing on mbarriers (UBLKCP, SYNCS), the Cholesky's trailing update runs on the FP64 tensor-core
+    path (DMMA), the posteriors' quadratic forms use packed FFMA2."""
+    import shutil
+    import subprocess
+    from fakebob_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+
+    def sass(fn):
+        return subprocess.run([cuobjdump, "-sass", "-fun", fn, _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    post = sass("_Z22fgmm_post_group_kernelPKfPKiS0_S0_S0_PKtS2_S2_S2_iiifPfS2_")
+    for mnemonic in ("UBLKCP", "SYNCS.PHASECHK", "FFMA2", "LDS.64"):
+        assert mnemonic in post, mnemonic
+    quad = sass("_Z20ivec_quad_tma_kernelPKfPKdPKiiiiPdS4_")
+    for mnemonic in ("UBLKCP", "SYNCS.PHASECHK", "DFMA"):
+        assert mnemonic in quad, mnemonic
+    solve = sass("_Z17ivec_solve_kernelPKdS0_iiiidPdPfPiPKi")
+    assert solve.count("DMMA") >= 64 and "UCGABAR" in solve
+
+
 def test_product_and_oracle_model_readers_agree(small_iv_tree):
     """The product's Kaldi file reader (fakebob_b200/kaldi_io.py) and the oracle's independent one (oracle/kaldi_files.py)
     parse every model file of the synthetic tree to the same arrays."""
