@@ -813,25 +813,34 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
 #define IV_QUAD_STAGE_COMPS 4
 #define IV_QUAD_COLS 256
 #define IV_QUAD_RING_BYTES (IV_QUAD_STAGES * IV_QUAD_STAGE_COMPS * IV_QUAD_COLS * 4)
-#define IV_QUAD_G_BYTES (64 * IV_BCHUNK * 8)
+#define IV_QUAD_GSTRIDE (IV_BCHUNK + 2)              // row stride (doubles) of the multiplier chunk: even (16-byte rows), and the
+                                                    // transposed stores of the gather hit 8 banks instead of 1
+#define IV_QUAD_G_BYTES (64 * IV_QUAD_GSTRIDE * 8)
 static inline size_t ivec_quad_tma_smem(int C) { return IV_QUAD_RING_BYTES + IV_QUAD_G_BYTES + 2 * IV_QUAD_STAGES * 8 + ((size_t)C + 4) * 4; }
 
-__global__ void __launch_bounds__(256, 2)
-ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gamma, const int *__restrict__ act_list, int B, int C,
-                     int n_packed, double *__restrict__ quad, const int *__restrict__ done_flag) {
-  if (done_flag && *done_flag) return;
+// One body for both sums: the streamed matrix W has RPC rows of `row_len` floats per component (quad: U, RPC = 1,
+// row_len = R (R + 1) / 2; lin: Sigma^-1 M, RPC = 72, row_len = R), the multiplier of row (c, d) for utterance b is
+// mult[(b C + c) RPC + d] (gamma, resp. the first-order statistics X), the components a CTA covers are the split-th part of
+// the chunk's active list, and out[(split B + b) row_len + e] receives its partial sum (quad: one split).
+template <int RPC>
+__device__ __forceinline__ void ivec_stream_body(const float *__restrict__ W, const double *__restrict__ mult,
+                                                 const int *__restrict__ act_list, int B, int C, int row_len, int n_splits,
+                                                 double *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char q_smem[];
   float *ring = reinterpret_cast<float *>(q_smem);
-  double (*s_g)[IV_BCHUNK] = reinterpret_cast<double (*)[IV_BCHUNK]>(q_smem + IV_QUAD_RING_BYTES);
+  double (*s_g)[IV_QUAD_GSTRIDE] = reinterpret_cast<double (*)[IV_QUAD_GSTRIDE]>(q_smem + IV_QUAD_RING_BYTES);
   uint64_t *bars = reinterpret_cast<uint64_t *>(q_smem + IV_QUAD_RING_BYTES + IV_QUAD_G_BYTES);
   int *s_list = reinterpret_cast<int *>(bars + 2 * IV_QUAD_STAGES);
   const uint32_t full0 = tma_smem_u32(bars), empty0 = tma_smem_u32(bars + IV_QUAD_STAGES);
   const int b0 = blockIdx.x * IV_BCHUNK;
   const int nb = min(IV_BCHUNK, B - b0);
   const int col0 = blockIdx.y * IV_QUAD_COLS;
+  const int split = blockIdx.z;
   const int *list = act_list + (size_t)blockIdx.x * (C + 1);
-  const int n_act = list[0];
-  for (int i = threadIdx.x; i < n_act; i += blockDim.x) s_list[i] = list[1 + i];
+  const int n_act_all = list[0];
+  const int a_lo = (int)((long long)n_act_all * split / n_splits), a_hi = (int)((long long)n_act_all * (split + 1) / n_splits);
+  const int n_act = (a_hi - a_lo) * RPC;             // items = rows of W this CTA streams, in (component, d) order
+  for (int i = threadIdx.x; i < a_hi - a_lo; i += blockDim.x) s_list[i] = list[1 + a_lo + i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < IV_QUAD_STAGES; ++s) {
       tma_bar_init(full0 + 8 * s, 1);
@@ -845,8 +854,12 @@ ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gam
   // thread 0 is also the producer: stage st + IV_QUAD_STAGES - 1 is issued right before stage st is consumed, into the slot
   // that stage st - 1 used (its "empty" barrier completes when all 8 warps have released it).  A separate producer warp
   // (288 threads) costs the second CTA per SM: 9 warps do not split evenly over the 4 sub-partitions' register files.
-  const uint32_t seg_bytes = (uint32_t)min(IV_QUAD_COLS, n_packed - col0) * 4u;
+  const uint32_t seg_bytes = (uint32_t)min(IV_QUAD_COLS, row_len - col0) * 4u;
   const uint32_t ring0 = tma_smem_u32(ring);
+  auto row_of = [&](int item) -> size_t {            // row index of W for an item
+    if (RPC == 1) return (size_t)s_list[item];
+    return (size_t)s_list[item / RPC] * RPC + (item % RPC);
+  };
   auto issue = [&](int st) {
     if (st >= n_stages) return;
     const int slot = st % IV_QUAD_STAGES, round = st / IV_QUAD_STAGES;
@@ -855,7 +868,7 @@ ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gam
     tma_bar_expect_tx(full0 + 8 * slot, nc * seg_bytes);
     for (int k = 0; k < nc; ++k)
       tma_bulk_g2s(ring0 + (uint32_t)((slot * IV_QUAD_STAGE_COMPS + k) * IV_QUAD_COLS * 4),
-                   U + (size_t)s_list[st * IV_QUAD_STAGE_COMPS + k] * n_packed + col0, seg_bytes, full0 + 8 * slot);
+                   W + row_of(st * IV_QUAD_STAGE_COMPS + k) * row_len + col0, seg_bytes, full0 + 8 * slot);
   };
   if (threadIdx.x == 0)
     for (int st0 = 0; st0 < IV_QUAD_STAGES - 1; ++st0) issue(st0);
@@ -867,24 +880,26 @@ ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gam
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-  // gamma gather of a 64-component chunk: element idx = threadIdx.x + 256 q -> component idx / 32, utterance idx % 32
+  // multiplier gather of a 64-item chunk: element idx = threadIdx.x + 256 q -> item idx % 64, utterance idx / 64, so that
+  // neighbouring threads read neighbouring rows of one utterance (lin: consecutive d of a component are contiguous in X;
+  // quad: neighbouring active components) instead of striding over the utterances
   double gnext[8];
   auto gather = [&](int a0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int idx = threadIdx.x + 256 * q, k = idx / IV_BCHUNK, i = idx - k * IV_BCHUNK;
-      gnext[q] = (i < nb && a0 + k < n_act) ? gamma[(size_t)(b0 + i) * C + s_list[a0 + k]] : 0.0;
+      const int idx = threadIdx.x + 256 * q, k = idx & 63, i = idx >> 6;
+      gnext[q] = (i < nb && a0 + k < n_act) ? mult[(size_t)(b0 + i) * C * RPC + row_of(a0 + k)] : 0.0;
     }
   };
   gather(0);
   int st = 0;
   for (int a0 = 0; a0 < n_act; a0 += 64) {
     const int n = min(64, n_act - a0);
-    __syncthreads();                                  // everybody finished reading the previous chunk's gammas
+    __syncthreads();                                  // everybody finished reading the previous chunk's multipliers
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int idx = threadIdx.x + 256 * q;
-      s_g[idx / IV_BCHUNK][idx % IV_BCHUNK] = gnext[q];
+      s_g[idx & 63][idx >> 6] = gnext[q];
     }
     __syncthreads();
     if (a0 + 64 < n_act) gather(a0 + 64);
@@ -913,17 +928,33 @@ ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gam
       if (lane == 0) tma_bar_arrive(empty0 + 8 * slot);
     }
   }
-  if (work && e0 < n_packed) {                         // n_packed % 4 == 0: a thread's four entries are inside or outside together
+  if (work && e0 < row_len) {                          // row_len % 4 == 0: a thread's four entries are inside or outside together
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int bi = ug * 8 + j;
       if (bi < nb) {
-        double2 *dst = reinterpret_cast<double2 *>(quad + (size_t)(b0 + bi) * n_packed + e0);
+        double2 *dst = reinterpret_cast<double2 *>(out + ((size_t)split * B + b0 + bi) * row_len + e0);
         dst[0] = make_double2(acc[0][j], acc[1][j]);
         dst[1] = make_double2(acc[2][j], acc[3][j]);
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256, 2)
+ivec_quad_tma_kernel(const float *__restrict__ U, const double *__restrict__ gamma, const int *__restrict__ act_list, int B, int C,
+                     int n_packed, double *__restrict__ quad, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  ivec_stream_body<1>(U, gamma, act_list, B, C, n_packed, 1, quad);
+}
+
+// lin through the same pipeline: grid (b-chunks, ceil(R / 256), splits); replaces ivec_lin_kernel whenever R % 4 == 0 (that
+// kernel has the structure ivec_quad_kernel had: four loads, wait, 128 DFMAs, 13 warps per SM).
+__global__ void __launch_bounds__(256, 2)
+ivec_lin_tma_kernel(const float *__restrict__ sim32, const double *__restrict__ Xs, const int *__restrict__ act_list, int B, int C,
+                    int R, int n_splits, double *__restrict__ part, const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  ivec_stream_body<FB_DIM>(sim32, Xs, act_list, B, C, R, n_splits, part);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1680,8 +1711,24 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
   const int bch = fb_div_up(B, IV_BCHUNK);
   const int lin_threads = ((4 * ((v->R + 3) / 4) + 31) / 32) * 32;
   ivec_active_kernel<<<bch, 1024, 0, ctx->stream>>>(v->gamma.p, B, v->C, v->act_list.p, done_flag);
-  ivec_lin_kernel<<<dim3(v->n_splits, bch), lin_threads, 0, ctx->stream>>>(v->sim32.p, v->Xs.p, v->act_list.p, B, v->C, v->R,
-                                                                          v->n_splits, v->lin_part.p, done_flag);
+  static const bool plain_lin = getenv("FB_IV_PLAIN_LIN") != nullptr;         // diagnostic: the register-staged kernel
+  static std::atomic<unsigned long long> attr_lin_mask{0};
+  if (fb_once_per_device(attr_lin_mask, ctx->device)) {
+    FB_CUDA(cudaFuncSetAttribute(ivec_lin_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  }
+  int n_splits = v->n_splits;                          // partial sums over the component range, added up by the solve
+  if ((v->R & 3) == 0 && !plain_lin && ivec_quad_tma_smem(v->C) <= 100 * 1024) {
+    const int colb = fb_div_up(v->R, IV_QUAD_COLS);
+    n_splits = (2 * ctx->num_sms) / (bch * colb);      // two CTAs per SM, one wave
+    if (n_splits < 1) n_splits = 1;
+    if (n_splits > v->n_splits) n_splits = v->n_splits;
+    ivec_lin_tma_kernel<<<dim3(bch, colb, n_splits), 256, ivec_quad_tma_smem(v->C), ctx->stream>>>(
+        v->sim32.p, v->Xs.p, v->act_list.p, B, v->C, v->R, n_splits, v->lin_part.p, done_flag);
+  } else {
+    ivec_lin_kernel<<<dim3(v->n_splits, bch), lin_threads, 0, ctx->stream>>>(v->sim32.p, v->Xs.p, v->act_list.p, B, v->C, v->R,
+                                                                            v->n_splits, v->lin_part.p, done_flag);
+  }
+  v->n_splits_used = n_splits;
   fb_prof_mark(ctx, 11);
   nv.next("fb:ivec_quad");
   static const bool plain_quad = getenv("FB_IV_PLAIN_QUAD") != nullptr;       // diagnostic: the register-staged kernel
@@ -1717,7 +1764,7 @@ int fb_run_ivector_flag(fb_ctx *ctx, const int *done_flag, bool with_plda) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FB_CUDA(cudaLaunchKernelEx(&cfg, ivec_solve_kernel, (const double *)v->quad.p, (const double *)v->lin_part.p, v->n_splits, B, v->R,
+    FB_CUDA(cudaLaunchKernelEx(&cfg, ivec_solve_kernel, (const double *)v->quad.p, (const double *)v->lin_part.p, v->n_splits_used, B, v->R,
                                v->n_packed, v->prior_offset, v->Awork.p, v->ivec.p, ctx->misc.p + 1, done_flag));
   }
   fb_prof_mark(ctx, 13);
@@ -1776,12 +1823,12 @@ extern "C" int fb_get_ivector_stats(fb_ctx *ctx, int b, double *gamma_host, doub
     FB_CUDA(cudaMemcpy(quad_host, v->quad.p + (size_t)b * v->n_packed, (size_t)v->n_packed * sizeof(double), cudaMemcpyDeviceToHost));
   if (lin_host) {
     std::vector<double> part((size_t)v->n_splits * v->R);
-    for (int s = 0; s < v->n_splits; ++s)
+    for (int s = 0; s < v->n_splits_used; ++s)
       FB_CUDA(cudaMemcpy(part.data() + (size_t)s * v->R, v->lin_part.p + ((size_t)s * ctx->B + b) * v->R, v->R * sizeof(double),
                          cudaMemcpyDeviceToHost));
     for (int r = 0; r < v->R; ++r) {
       double acc = 0.0;
-      for (int s = 0; s < v->n_splits; ++s) acc += part[(size_t)s * v->R + r];
+      for (int s = 0; s < v->n_splits_used; ++s) acc += part[(size_t)s * v->R + r];
       lin_host[r] = acc;
     }
   }

@@ -3,7 +3,7 @@
 #include "fb_common.cuh"
 
 struct FbIvector {
-  int C = 0, R = 0, L = 0, K = 0, n_packed = 0, lda_cols = 0, n_splits = 0;
+  int C = 0, R = 0, L = 0, K = 0, n_packed = 0, lda_cols = 0, n_splits = 0, n_splits_used = 0;
   double prior_offset = 0.0;
   float min_post = 0.025f;
   bool have_ubm = false, have_ie = false, have_backend = false;
