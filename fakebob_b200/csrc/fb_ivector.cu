@@ -804,13 +804,14 @@ ivec_quad_kernel(const float *__restrict__ U, const double *__restrict__ gamma, 
 // The same sum with the rows of U staged by the TMA engine (used whenever n_packed is a multiple of 4, i.e. 16-byte
 // aligned row segments).  ncu of the kernel above at C3: 282 us, issue slots 32 % busy, 5.4 warps stalled on global loads per
 // issued instruction -- a thread loads four rows, waits, then runs its 128 DFMAs, and with 126 registers only 16 warps per SM
-// hide that.  Here one thread streams the active rows (one bulk copy of this CTA's column segment per component, four
-// components per stage, IV_QUAD_STAGES stages in flight, completion on mbarriers) while 8 consumer warps only read shared
+// hide that.  Here one thread streams the active rows (one bulk copy of this CTA's column segment per component, sixteen
+// components per stage -- with four, the per-stage barrier traffic cost 17 %: 196 -> 162 us -- IV_QUAD_STAGES stages in
+// flight, completion on mbarriers) while 8 consumer warps only read shared
 // memory and feed the FP64 pipe; the gammas of the next 64 components are prefetched into registers during the current
 // 64.  Grid (b-chunks, column blocks): the CTAs of one column block run side by side, so its rows come from HBM once and
 // from L2 for the other utterance chunks.  Arithmetic and summation order per entry are those of the kernel above.
-#define IV_QUAD_STAGES 12
-#define IV_QUAD_STAGE_COMPS 4
+#define IV_QUAD_STAGES 4
+#define IV_QUAD_STAGE_COMPS 16
 #define IV_QUAD_COLS 256
 #define IV_QUAD_RING_BYTES (IV_QUAD_STAGES * IV_QUAD_STAGE_COMPS * IV_QUAD_COLS * 4)
 #define IV_QUAD_GSTRIDE (IV_BCHUNK + 2)              // row stride (doubles) of the multiplier chunk: even (16-byte rows), and the
