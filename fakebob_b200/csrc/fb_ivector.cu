@@ -255,20 +255,21 @@ fgmm_post_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, 
 #define IV_RPG (IV_GROUP / 2)                       // rows per row group (two row groups)
 #define IV_SLICE_PAIRS ((IV_PAIRS + IV_ES - 1) / IV_ES)        // 338
 #define IV_LP ((IV_SLICE_PAIRS + 31) / 32)          // 11 register pairs per lane and row
-#define IV_POST_STAGES 8                            // covariance blocks in flight (a bulk copy of 10.8 KB takes ~2 k cycles to land,
-                                                    // a component ~0.3 k cycles to consume: with 4 the warps waited 16 % of the time)
-#define IV_COMB_LAG 4                               // a component's partials are combined this many components later
-#define IV_PSLOTS 16                                // partial-sum slots, >= IV_POST_STAGES + IV_COMB_LAG (see the slot-reuse argument)
+#define IV_POST_NCS 2                               // components per ring stage: both are multiplied in one pass over the row
+                                                    // multipliers (8 independent FFMA2 chains) and share the barrier traffic
+#define IV_POST_STAGES 4                            // stages in flight (2 x 10.8 KB each; a bulk copy takes ~2 k cycles to land)
+#define IV_COMB_LAG 2                               // a stage's partials are combined this many stages later
+#define IV_PSLOTS 8                                 // partial-sum slots, >= IV_POST_STAGES + IV_COMB_LAG (see the slot-reuse argument)
 static_assert(IV_PSLOTS >= IV_POST_STAGES + IV_COMB_LAG, "a partial slot must be combined before the ring lets anybody refill it");
 static_assert(IV_PACKED % 4 == 0 && FB_DIM % 4 == 0, "bulk copies need 16-byte aligned component blocks of 16 n bytes");
 static_assert(IV_PACKED % 2 == 0 && IV_ENT % 2 == 0, "pairs of entries");
 
 struct __align__(16) PostSmem {
-  float S[IV_POST_STAGES][IV_ENT];
+  float S[IV_POST_STAGES][IV_POST_NCS][IV_ENT];
   float gc[IV_GROUP * IV_NSEL];
   float x[IV_GROUP][FB_DIM];
   float ll[IV_GROUP][IV_NSEL];
-  float part[IV_PSLOTS][2][IV_ES][IV_RPG];
+  float part[IV_PSLOTS][IV_POST_NCS][2][IV_ES][IV_RPG];
   unsigned bitmap[128];                             // C <= 4096
   unsigned short prefix[128];                       // union members before bitmap word i
   int list[IV_GROUP * IV_NSEL];
@@ -381,73 +382,95 @@ fgmm_post_group_kernel(const float *__restrict__ feats, const int *__restrict__ 
   }
   if (lane < IV_NSEL) sm.ll[w][lane] = -INFINITY;
   __syncthreads();
-  auto issue = [&](int ui) {
-    if (ui >= n_union) return;
-    const int slot = ui % IV_POST_STAGES, round = ui / IV_POST_STAGES;
+  const int n_it = (n_union + IV_POST_NCS - 1) / IV_POST_NCS;       // ring stages: IV_POST_NCS union members each
+  auto issue = [&](int it) {
+    if (it >= n_it) return;
+    const int slot = it % IV_POST_STAGES, round = it / IV_POST_STAGES;
     if (round > 0) { tma_bar_wait(empty0 + 8 * slot, (round - 1) & 1); tma_fence_proxy_async(); }
-    const int c = sm.list[ui];
-    tma_bar_expect_tx(full0 + 8 * slot, IV_ENT * 4);
-    tma_bulk_g2s(tma_smem_u32(sm.S[slot]), inv_covars_packed + (size_t)c * IV_PACKED, IV_PACKED * 4, full0 + 8 * slot);
-    tma_bulk_g2s(tma_smem_u32(sm.S[slot] + IV_PACKED), means_invcovars + (size_t)c * FB_DIM, FB_DIM * 4, full0 + 8 * slot);
+    const int nc = min(IV_POST_NCS, n_union - it * IV_POST_NCS);
+    tma_bar_expect_tx(full0 + 8 * slot, nc * IV_ENT * 4);
+    for (int k = 0; k < nc; ++k) {
+      const int c = sm.list[it * IV_POST_NCS + k];
+      tma_bulk_g2s(tma_smem_u32(sm.S[slot][k]), inv_covars_packed + (size_t)c * IV_PACKED, IV_PACKED * 4, full0 + 8 * slot);
+      tma_bulk_g2s(tma_smem_u32(sm.S[slot][k] + IV_PACKED), means_invcovars + (size_t)c * FB_DIM, FB_DIM * 4, full0 + 8 * slot);
+    }
   };
   // the four slice partials of (row r, union member uc) -> log-likelihood, in slice order
-  auto combine = [&](int uc) {
-    const int ps = uc % IV_PSLOTS;
-    tma_bar_wait(pfull0 + 8 * ps, (uc / IV_PSLOTS) & 1);
+  auto combine = [&](int itc) {
+    const int ps = itc % IV_PSLOTS;
+    tma_bar_wait(pfull0 + 8 * ps, (itc / IV_PSLOTS) & 1);
     if (lane < IV_GROUP) {
-      const unsigned p = reinterpret_cast<const unsigned char *>(&sm.pos[uc][0])[lane];
-      if (p != 0xFFu) {
-        const int g = lane / IV_RPG, k = lane % IV_RPG;
-        const float q = ((sm.part[ps][g][0][k] + sm.part[ps][g][1][k]) + sm.part[ps][g][2][k]) + sm.part[ps][g][3][k];
-        sm.ll[lane][p] = sm.gc[uc] - q;               // gconst + lin - q
+#pragma unroll
+      for (int k = 0; k < IV_POST_NCS; ++k) {
+        const int uc = itc * IV_POST_NCS + k;
+        if (uc < n_union) {
+          const unsigned p = reinterpret_cast<const unsigned char *>(&sm.pos[uc][0])[lane];
+          if (p != 0xFFu) {
+            const int g2 = lane / IV_RPG, r = lane % IV_RPG;
+            const float q = ((sm.part[ps][k][g2][0][r] + sm.part[ps][k][g2][1][r]) + sm.part[ps][k][g2][2][r]) + sm.part[ps][k][g2][3][r];
+            sm.ll[lane][p] = sm.gc[uc] - q;           // gconst + lin - q
+          }
+        }
       }
     }
   };
   if (threadIdx.x == 0)
     for (int u0 = 0; u0 < IV_POST_STAGES - 1; ++u0) issue(u0);
-  for (int ui = 0; ui < n_union; ++ui) {
-    const int slot = ui % IV_POST_STAGES;
-    const bool need = sm.pos[ui][rg] != 0xFFFFFFFFu;  // some row of my group selected it
-    if (threadIdx.x == 0) issue(ui + IV_POST_STAGES - 1);            // into the slot component ui - 1 used
-    tma_bar_wait(full0 + 8 * slot, (ui / IV_POST_STAGES) & 1);
-    if (need) {
-      const float2 *S2 = reinterpret_cast<const float2 *>(sm.S[slot]) + es * IV_SLICE_PAIRS + lane;
-      float2 acc[IV_RPG];
+  const bool hi = (lane & 16) != 0, b8 = (lane & 8) != 0;
+  // 4 rows x 32 lanes -> one total per row: exchange halves (rows 0,1 | 2,3), then (row a | row b), then a butterfly
+  auto reduce4 = [&](const float2 (&acc)[IV_RPG]) {
+    const float t0 = acc[0].x + acc[0].y, t1 = acc[1].x + acc[1].y, t2 = acc[2].x + acc[2].y, t3 = acc[3].x + acc[3].y;
+    float k0 = hi ? t2 : t0, k1 = hi ? t3 : t1;
+    k0 += __shfl_xor_sync(0xffffffffu, hi ? t0 : t2, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, hi ? t1 : t3, 16);
+    float kk = b8 ? k1 : k0;
+    kk += __shfl_xor_sync(0xffffffffu, b8 ? k0 : k1, 8);
+    kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+    kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+    kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+    return kk;
+  };
+  for (int it = 0; it < n_it; ++it) {
+    const int slot = it % IV_POST_STAGES;
+    if (threadIdx.x == 0) issue(it + IV_POST_STAGES - 1);            // into the slot stage it - 1 used
+    tma_bar_wait(full0 + 8 * slot, (it / IV_POST_STAGES) & 1);
+    {
+      // both components of the stage in one pass (an absent second one of the last stage reads stale, finite data and is
+      // never combined); a row group none of whose rows selected a component computes it anyway (~1 % of the cases)
+      const float2 *Sa = reinterpret_cast<const float2 *>(sm.S[slot][0]) + es * IV_SLICE_PAIRS + lane;
+      const float2 *Sb = reinterpret_cast<const float2 *>(sm.S[slot][1]) + es * IV_SLICE_PAIRS + lane;
+      float2 acca[IV_RPG], accb[IV_RPG];
 #pragma unroll
-      for (int k = 0; k < IV_RPG; ++k) acc[k] = make_float2(0.f, 0.f);
+      for (int k = 0; k < IV_RPG; ++k) acca[k] = accb[k] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int m = 0; m < IV_LP; ++m) {
         // only the last pair index is partly outside the slice (xx is zero there, but the buffer holds no defined value)
         const bool inside = 32 * m + 31 < IV_SLICE_PAIRS && (IV_ES - 1) * IV_SLICE_PAIRS + 32 * m + 31 < IV_PAIRS;
         if (inside || (lane + 32 * m < IV_SLICE_PAIRS && es * IV_SLICE_PAIRS + lane + 32 * m < IV_PAIRS)) {
-          const float2 s2 = S2[32 * m];
+          const float2 sa = Sa[32 * m], sb = Sb[32 * m];
 #pragma unroll
-          for (int k = 0; k < IV_RPG; ++k) acc[k] = __ffma2_rn(s2, xx[k][m], acc[k]);
+          for (int k = 0; k < IV_RPG; ++k) {
+            acca[k] = __ffma2_rn(sa, xx[k][m], acca[k]);
+            accb[k] = __ffma2_rn(sb, xx[k][m], accb[k]);
+          }
         }
       }
-      // 4 rows x 32 lanes -> one total per row: exchange halves (rows 0,1 | 2,3), then (row a | row b), then a butterfly
-      const float t0 = acc[0].x + acc[0].y, t1 = acc[1].x + acc[1].y, t2 = acc[2].x + acc[2].y, t3 = acc[3].x + acc[3].y;
-      const bool hi = (lane & 16) != 0;
-      float k0 = hi ? t2 : t0, k1 = hi ? t3 : t1;
-      k0 += __shfl_xor_sync(0xffffffffu, hi ? t0 : t2, 16);
-      k1 += __shfl_xor_sync(0xffffffffu, hi ? t1 : t3, 16);
-      const bool b8 = (lane & 8) != 0;
-      float kk = b8 ? k1 : k0;
-      kk += __shfl_xor_sync(0xffffffffu, b8 ? k0 : k1, 8);
-      kk += __shfl_xor_sync(0xffffffffu, kk, 4);
-      kk += __shfl_xor_sync(0xffffffffu, kk, 2);
-      kk += __shfl_xor_sync(0xffffffffu, kk, 1);
-      if ((lane & 7) == 0) sm.part[ui % IV_PSLOTS][rg][es][(hi ? 2 : 0) + (b8 ? 1 : 0)] = kk;
+      const float ka = reduce4(acca), kb = reduce4(accb);
+      if ((lane & 7) == 0) {
+        const int r = (hi ? 2 : 0) + (b8 ? 1 : 0);
+        sm.part[it % IV_PSLOTS][0][rg][es][r] = ka;
+        sm.part[it % IV_PSLOTS][1][rg][es][r] = kb;
+      }
     }
-    if (ui >= IV_COMB_LAG && ((ui - IV_COMB_LAG) % IV_GROUP) == w) combine(ui - IV_COMB_LAG);
+    if (it >= IV_COMB_LAG && ((it - IV_COMB_LAG) % IV_GROUP) == w) combine(it - IV_COMB_LAG);
     __syncwarp();
     if (lane == 0) {
-      tma_bar_arrive(pfull0 + 8 * (ui % IV_PSLOTS));
+      tma_bar_arrive(pfull0 + 8 * (it % IV_PSLOTS));
       tma_bar_arrive(empty0 + 8 * slot);
     }
   }
-  for (int uc = max(0, n_union - IV_COMB_LAG); uc < n_union; ++uc)
-    if ((uc % IV_GROUP) == w) combine(uc);
+  for (int itc = max(0, n_it - IV_COMB_LAG); itc < n_it; ++itc)
+    if ((itc % IV_GROUP) == w) combine(itc);
   __syncthreads();
   if (row < 0) return;
   const float my_ll = (lane < IV_NSEL) ? sm.ll[w][lane] : -INFINITY;
