@@ -370,7 +370,7 @@ def rooflines(name, prof, rows, n_models, peaks, active_frac=None, b_local=None)
     else:
         tensor("gmm", 2.0 * rows * N_MIX * 144, "gmm_umma_kernel<STORE>", "Gaussian selection on the diagonalised full UBM: 2*rows*C*(2D)")
         af = active_frac if active_frac else 1.0
-        mem("ivec_lin", 4.0 * N_MIX * 72 * IV_R * af, "ivec_lin_kernel",
+        mem("ivec_lin", 4.0 * N_MIX * 72 * IV_R * af, "ivec_lin_tma_kernel",
             "bytes = active components x 72 x R x 4 (fp32 Sigma^-1 M rows of the components with gamma != 0; %.0f %% active)" % (100 * af))
         mem("ivec_quad", 4.0 * N_MIX * (IV_R * (IV_R + 1) // 2) * af, "ivec_quad_tma_kernel",
             "bytes = active components x R(R+1)/2 x 4 (fp32 U rows of the components with gamma != 0; %.0f %% active)" % (100 * af))
