@@ -40,8 +40,7 @@ __global__ void __launch_bounds__(256, 3)
 gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C, int *__restrict__ gsel,
                const int *__restrict__ done_flag) {
   if (done_flag && *done_flag) return;
-  __shared__ float s_val[8][IV_CAND];
-  __shared__ int s_idx[8][IV_CAND];
+  __shared__ unsigned long long s_key[8][IV_CAND];
   const int w = threadIdx.x >> 5;
   const int row = blockIdx.x * 8 + w;
   const int lane = threadIdx.x & 31;
@@ -104,30 +103,27 @@ gselect_kernel(const float *__restrict__ ll, const int *__restrict__ misc, int C
       if (lane >= o) incl += up;
     }
     int pos = incl - mine;
-    // a lane passes one or two values: walk its mask and re-read them (L1 / L2 hits) instead of testing all 64 registers
-    for (unsigned m = m_lo; m; m &= m - 1) {
-      const int i = __ffs(m) - 1;
-      s_val[w][pos] = src[lane + 32 * i]; s_idx[w][pos] = lane + 32 * i; ++pos;
-    }
-    for (unsigned m = m_hi; m; m &= m - 1) {
-      const int i = 32 + __ffs(m) - 1;
-      s_val[w][pos] = src[lane + 32 * i]; s_idx[w][pos] = lane + 32 * i; ++pos;
-    }
+    // a lane passes one or two values: walk its mask and re-read them (L1 / L2 hits) instead of testing all 64 registers.
+    // A candidate is stored as ONE sortable 64-bit key: order-preserving bits of the value above, inverted component index
+    // below, so "value descending, index ascending" is a plain unsigned comparison and the ranking loop below costs one
+    // 64-bit load and two compare / add pairs per step for both candidates of a lane.
+    auto key_of = [&](int i) {
+      const unsigned u = __float_as_uint(src[lane + 32 * i]);
+      const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);       // monotone map float -> unsigned
+      return ((unsigned long long)ord << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)(lane + 32 * i));
+    };
+    for (unsigned m = m_lo; m; m &= m - 1) s_key[w][pos++] = key_of(__ffs(m) - 1);
+    for (unsigned m = m_hi; m; m &= m - 1) s_key[w][pos++] = key_of(32 + __ffs(m) - 1);
     __syncwarp();
-#pragma unroll
-    for (int h = 0; h < IV_CAND / 32; ++h) {
-      const int me = lane + 32 * h;
-      if (me < cnt) {
-        const float a = s_val[w][me];
-        const int ai = s_idx[w][me];
-        int rank = 0;
-        for (int j = 0; j < cnt; ++j) {
-          const float o = s_val[w][j];
-          rank += (o > a || (o == a && s_idx[w][j] < ai)) ? 1 : 0;
-        }
-        if (rank < IV_NSEL) gsel[(size_t)row * IV_NSEL + rank] = ai;
-      }
+    const unsigned long long k0 = (lane < cnt) ? s_key[w][lane] : 0ull, k1 = (lane + 32 < cnt) ? s_key[w][lane + 32] : 0ull;
+    int rank0 = 0, rank1 = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const unsigned long long o = s_key[w][j];
+      rank0 += (o > k0) ? 1 : 0;
+      rank1 += (o > k1) ? 1 : 0;
     }
+    if (lane < cnt && rank0 < IV_NSEL) gsel[(size_t)row * IV_NSEL + rank0] = (int)(0xFFFFFFFFu - (unsigned)k0);
+    if (lane + 32 < cnt && rank1 < IV_NSEL) gsel[(size_t)row * IV_NSEL + rank1] = (int)(0xFFFFFFFFu - (unsigned)k1);
     return;
   }
   int bi = 0;                                        // slow path: this lane's arg-max (first maximum)
