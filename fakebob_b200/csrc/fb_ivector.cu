@@ -232,16 +232,20 @@ fgmm_post_kernel(const float *__restrict__ feats, const int *__restrict__ gsel, 
 //    same components: the CTA stages the UNION of its rows' selections, each component once (~25 instead of 8 x 20).  Any
 //    batch is handled correctly: rows that share no component simply do not share loads;
 //  * a component is staged as one block [packed inverse covariance | mean x inverse covariance] (2700 floats) by two bulk
-//    copies of the TMA engine that complete on the slot's "full" mbarrier (ring of IV_POST_STAGES slots, released through
-//    "empty" mbarriers; thread 0 issues stage ui + 3 right before it consumes stage ui -- a separate producer warp was
-//    measured slower: 9 warps of 110 registers do not fit twice into the SM's four register files);
+//    copies of the TMA engine that complete on the slot's "full" mbarrier; a ring stage holds IV_POST_NCS components
+//    (ring of IV_POST_STAGES stages, released through "empty" mbarriers; thread 0 issues stage it + 3 right before it
+//    consumes stage it -- a separate producer warp was measured slower: 9 warps of 110 registers do not fit twice into
+//    the SM's four register files);
 //  * the multipliers of a row -- x_r x_c (halved on the diagonal) against the covariance entries, -x_d against the linear
 //    entries, so one pass gives q - lin -- live in REGISTERS as pairs, one 64-bit shared-memory load + one packed FFMA2 per
 //    two entries;
 //  * warp w = (row group w / 4, entry slice w % 4): it multiplies ONE QUARTER of the staged block with FOUR rows, so a
 //    staged value is read from shared memory twice per CTA instead of once per selecting row (the row-per-warp version
 //    moved 5 GB through shared memory per launch, half of its run time).  The four slice partials of a (row, component)
-//    meet in shared memory (fixed order: deterministic) IV_COMB_LAG components later, combined by warp (component % 8).
+//    meet in shared memory (fixed order: deterministic) IV_COMB_LAG stages later, combined by warp (stage % 8).
+//    Slot reuse: warp (it % 8) combines stage it inside its iteration it + IV_COMB_LAG, BEFORE it releases that stage's ring
+//    slot; partial slot it % IV_PSLOTS is written again in iteration it + IV_PSLOTS, whose data thread 0 only requests
+//    after every warp has released stage it + IV_PSLOTS - IV_POST_STAGES >= it + IV_COMB_LAG -- so the combine is done.
 // Summation order differs from fgmm_post_kernel (float rounding only); selection, soft-max and pruning are the same.
 // ------------------------------------------------------------------------------------------------
 #define IV_GROUP 8
