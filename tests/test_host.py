@@ -457,3 +457,36 @@ def test_product_and_oracle_model_readers_agree(small_iv_tree):
         assert np.array_equal(np.asarray(a[k]), b[k])
     assert np.array_equal(np.asarray(kaldi_io.read_vector(os.path.join(pre, "mean.vec"))), okf.read_vector(os.path.join(pre, "mean.vec")))
     assert np.array_equal(np.asarray(kaldi_io.read_matrix(os.path.join(pre, "transform.mat"))), okf.read_matrix(os.path.join(pre, "transform.mat")))
+
+
+def test_bench_rooflines_bookkeeping():
+    """bench.py's per-kernel roofline table on synthetic stage times: the GMM contraction's algorithmic FLOPs (SURVEY 8d:
+    2 rows C 2D per model), the float64 kernels' fractions of the measured FMA rate, and the traffic table lookup."""
+    import importlib
+    import json
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    peaks = {"bf16_tflops": 1600.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6500.0}
+    rows = 23205
+    prof = {"gmm": (0.1 * 3, 3), "mfcc": (0.05 * 3, 3), "feats": (0.03 * 3, 3)}
+    roof, ms = bench.rooflines("C2", prof, rows, 6, peaks)
+    assert abs(ms["gmm"] - 0.1) < 1e-12
+    flops = 2.0 * rows * 2048 * 144 * 6
+    assert roof["gmm"]["algorithmic_flops_per_launch"] == flops
+    assert abs(roof["gmm"]["achieved"] - flops / 0.1e-3 / 1e12) < 1e-6 and roof["gmm"]["peak"] == 1600.0
+    assert abs(roof["gmm"]["frac"] * 1600.0 - roof["gmm"]["frac_of_sustained_peak"] * 1400.0) < 1e-6
+    prof3 = {k: (v * 2, 2) for k, v in {"gmm": 0.13, "ivec_lin": 0.1, "ivec_quad": 0.16, "ivec_solve": 0.37, "fgmm_post": 0.23,
+                                       "gselect": 0.05, "mfcc": 0.06, "feats": 0.03}.items()}
+    roof3, _ = bench.rooflines("C3", prof3, rows, 1, peaks, active_frac=0.08)
+    for k in ("ivec_lin", "ivec_quad", "ivec_solve"):
+        f = roof3[k]["fp64"]
+        assert f["peak_tfma_per_s"] == bench.FP64_TFMA_PEAK and 0.0 < f["frac"] < 1.0
+    b = bench.CONFIGS["C3"]["S"] + 1
+    assert roof3["ivec_solve"]["fp64"]["algorithmic_fma_per_launch"] == b * 400 ** 3 / 6.0
+    assert roof3["ivec_quad"]["kernel"] == "ivec_quad_tma_kernel" and roof3["ivec_lin"]["kernel"] == "ivec_lin_tma_kernel"
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+        table = json.load(f)
+    for kernel in ("gmm_umma_kernel", "ivec_solve_kernel", "ivec_quad_tma_kernel", "ivec_lin_tma_kernel", "fgmm_post_group_kernel",
+                   "gselect_kernel", "mfcc_kernel", "feats_kernel"):
+        assert kernel in table and table[kernel]["dram_bytes_per_launch"] > 0
+        assert bench.load_traffic(kernel)[0] == table[kernel]["dram_bytes_per_launch"]
