@@ -133,3 +133,41 @@ def test_ivector_path_is_bitwise_reproducible(iv_osi):
         else:
             for a, b in zip(ref, cur):
                 assert np.array_equal(a, b), "repetition %d differs" % rep
+
+
+def test_register_staged_fallback_kernels_agree_with_the_tma_staged_ones(small_iv_tree):
+    """The TMA-staged posterior / quad / lin kernels replaced register-staged ones that remain as the fallback for extractor
+    sizes without 16-byte aligned rows (and as diagnostics).  Same batch through both sets, each in
+    its own process (the switches are read once): same scores and i-vectors up to float rounding of the posteriors."""
+    import json
+    import os
+    import subprocess
+    import sys
+    t = small_iv_tree
+    code = r'''
+import json, sys, os
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np
+from conftest import test_audio as make_audio
+from fakebob_b200.engine import to_audio_list, IvectorEngine
+eng = IvectorEngine(%(pre)r)
+eng.set_enrolled(np.load(%(enr)r))
+lst = to_audio_list([make_audio(81, 0), make_audio(82, 1, n=24000), make_audio(83, 2, n=40000)])
+scores, ivs = eng.score_plda(lst, want_ivectors=True)
+print(json.dumps({"scores": np.asarray(scores).tolist(), "ivs": np.asarray(ivs).tolist()}))
+'''
+    enr = os.path.join(t["root"], "enrolled_for_fallback_test.npy")
+    np.save(enr, np.asarray(t["enrolled"], dtype=np.float32))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = code % {"root": root, "pre": t["pre_model_dir"], "enr": enr}
+    out = {}
+    for name, extra in (("tma", {}), ("plain", {"FB_IV_PLAIN_POST": "1", "FB_IV_PLAIN_QUAD": "1", "FB_IV_PLAIN_LIN": "1"})):
+        env = dict(os.environ)
+        env.update(extra)
+        r = subprocess.run([sys.executable, "-c", src], env=env, capture_output=True, text=True, timeout=240)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    a, b = np.array(out["tma"]["ivs"]), np.array(out["plain"]["ivs"])
+    assert np.abs(a - b).max() < 2e-3 * max(1.0, np.abs(b).max())
+    sa, sb = np.array(out["tma"]["scores"]), np.array(out["plain"]["scores"])
+    assert np.abs(sa - sb).max() < 5e-3
