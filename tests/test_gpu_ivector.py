@@ -171,3 +171,17 @@ print(json.dumps({"scores": np.asarray(scores).tolist(), "ivs": np.asarray(ivs).
     assert np.abs(a - b).max() < 2e-3 * max(1.0, np.abs(b).max())
     sa, sb = np.array(out["tma"]["scores"]), np.array(out["plain"]["scores"])
     assert np.abs(sa - sb).max() < 5e-3
+
+
+def test_large_batch_rows_equal_single_utterance_results(iv_osi):
+    """70 utterances in one call (three 32-utterance chunks in the quad / lin kernels, nine 8-row groups per frame index in
+    the posterior kernel, active lists that are unions over a chunk) against the same utterances scored alone: an
+    utterance's result must not depend on what else is in the batch."""
+    from fakebob_b200.engine import to_audio_list
+    lst = to_audio_list([make_audio(200 + i, i % 5, n=12000 + 800 * (i % 7)) for i in range(70)])
+    scores, ivs = iv_osi._engine.score_plda(lst, want_ivectors=True)
+    assert np.isfinite(scores).all() and np.isfinite(ivs).all()
+    for i in (0, 7, 31, 32, 33, 63, 64, 69):
+        s1, v1 = iv_osi._engine.score_plda([lst[i]], want_ivectors=True)
+        assert np.abs(v1[0] - ivs[i]).max() < 1e-4 * max(1.0, np.abs(v1[0]).max()), i
+        assert np.abs(s1[0] - scores[i]).max() < 1e-3, i
